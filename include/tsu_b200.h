@@ -1,0 +1,191 @@
+/*
+ * tsu_b200.h - C-ABI of libtsu_b200.so: B200 (sm_100a) kernels for the data-parallel hot path
+ * of tsu-emulator (heat-bath Gibbs spin updates over Ising models, batched Langevin steps).
+ *
+ * The reference (Arsham-001/tsu-emulator) is pure Python/NumPy and has no FFI of its own; the
+ * boundary it exposes is its Python class API.  Each entry point below names the reference
+ * interface (file:line under /root/reference) whose inner loop it replaces.  The Python host
+ * layer (tsu_emulator_b200/*.py) binds these with ctypes and mirrors the reference classes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every d_* pointer is DEVICE memory owned by the caller
+ *     (torch allocates it), h_* pointers are host memory; `stream` is a cudaStream_t passed as
+ *     uintptr_t (0 = default stream).  Nothing is allocated or freed behind the caller's back
+ *     and no call synchronises the device.
+ *   - return value: 0 = ok; negative = TSU_ERR_* (invalid argument, ...); positive = the
+ *     cudaError_t of the launch.  Nothing throws.
+ *   - spins are stored as bits: bit 1 <=> s = +1 (tsu/models/ising.py:119-125).
+ *   - all randomness is counter-based Philox4x32-10 keyed by (seed, coordinates); it replaces the
+ *     global numpy stream (tsu/gibbs.py:126,157,201; tsu/core.py:78,143).
+ */
+#ifndef TSU_B200_H
+#define TSU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSU_OK 0
+#define TSU_ERR_INVALID_ARG (-1)
+#define TSU_ERR_UNSUPPORTED (-2)
+#define TSU_ERR_NO_DEVICE (-3)
+
+#define TSU_B200_ABI_VERSION 1
+
+int tsu_version(void);
+const char* tsu_error_string(int code);
+/* number of SMs / compute capability of the current device; TSU_ERR_NO_DEVICE without a GPU */
+int tsu_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------ Philox4x32-10 ---- */
+/* host-side single block (known-answer tests; same code as the device generator) */
+void tsu_philox4x32_10_host(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* d_out[i] = word (i&3) of Philox(counter=(i>>2 lo, i>>2 hi, offset lo, 'FILL'), key=seed) */
+int tsu_philox_fill_u32(uint32_t* d_out, uint64_t n, uint64_t seed, uint32_t offset, uintptr_t stream);
+
+/* ------------------------------------------------------------------ 2-D lattice ------- */
+/*
+ * Replaces the inner loop of GibbsSampler.gibbs_sweep / sample_conditional
+ * (tsu/gibbs.py:102-162) for the nearest-neighbour lattice that IsingGrid wires up
+ * (tsu/models/ising.py:320-361), and README's IsingModel2D.gibbs_update (README.md:116-131).
+ *
+ * State layout (uint32 words): state[replica][colour][row][wpr]
+ *   colour = (row_global + col) & 1 (0 = "black", updated first); within a row the sites of one
+ *   colour are compressed: col = 2k + ((row_global + colour) & 1); word w holds k in [32w,32w+32),
+ *   lane b = k & 31.  wpr = tsu_ising2d_words_per_row(cols) (padded to 4 words = 16 bytes);
+ *   padding bits are always 0.
+ *
+ * Threshold table `lut` (uint32[32] per table): lut[d*5+u] = ceil(p * 2^32) for a site with d
+ *   existing neighbours of which u are up, p = sigmoid(h_bit/T) computed by the HOST in float64
+ *   with the reference's formula (tsu/gibbs.py:61-77,124-125); lut[25] bit (d*5+u) set means
+ *   p == 1.0 (always accept).  New bit = 1 iff uniform_u32 < threshold, which is exactly
+ *   `np.random.rand() < prob` of tsu/gibbs.py:126 for uniforms of the form k / 2^32.
+ *   d_lut holds n tables; d_lut_index[replica] picks one (NULL: all replicas use table 0).
+ */
+int64_t tsu_ising2d_words_per_row(int cols);
+int64_t tsu_ising2d_state_words(int rows, int cols); /* per replica: 2 * rows * wpr */
+
+/* iid Bernoulli(1/2) configuration from Philox (kind=2 stream); replaces np.random.randint(0,2,N)
+ * of tsu/gibbs.py:201.  row0 = global index of local row 0, replica0 = global index of replica 0. */
+int tsu_ising2d_init_random(uint32_t* d_state, int n_replicas, int rows, int cols, uint64_t seed,
+                            uint32_t replica0, int row0, uintptr_t stream);
+/* int8 spins[replica][row][col] (bit = value > 0) <-> packed state */
+int tsu_ising2d_pack(const int8_t* d_spins, uint32_t* d_state, int n_replicas, int rows, int cols,
+                     uintptr_t stream);
+int tsu_ising2d_unpack(const uint32_t* d_state, int8_t* d_spins, int n_replicas, int rows, int cols,
+                       int as_pm1, uintptr_t stream);
+
+/* One half-sweep: every site of `colour` is resampled (heat bath).  Uniforms come from the
+ * in-register Philox stream (seed, replica0+replica, sweep, row0+row, word).
+ * d_halo_top / d_halo_bot: [n_replicas][wpr] words of the OPPOSITE colour for global rows
+ * row0-1 / row0+rows (row-slab sharding); NULL = wrap inside the local array if wrap_rows,
+ * else open edge.  wrap_cols: periodic in the column direction (cols must be even). */
+int tsu_ising2d_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows,
+                           int wrap_cols, int colour, const uint32_t* d_lut,
+                           const int32_t* d_lut_index, uint64_t seed, uint32_t sweep,
+                           uint32_t replica0, int row0, const uint32_t* d_halo_top,
+                           const uint32_t* d_halo_bot, uintptr_t stream);
+/* n_sweeps full sweeps (black then white), sweep indices sweep0 .. sweep0+n_sweeps-1, no halos. */
+int tsu_ising2d_sweeps(uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows,
+                       int wrap_cols, const uint32_t* d_lut, const int32_t* d_lut_index,
+                       uint64_t seed, uint32_t sweep0, int n_sweeps, uint32_t replica0,
+                       uintptr_t stream);
+/* Parity mode: same update, but the uniform of site (replica,row,col) is read from
+ * d_uniforms[replica][row][col] (uint32 k meaning k/2^32) instead of Philox. */
+int tsu_ising2d_half_sweep_injected(uint32_t* d_state, int n_replicas, int rows, int cols,
+                                    int wrap_rows, int wrap_cols, int colour, const uint32_t* d_lut,
+                                    const int32_t* d_lut_index, const uint32_t* d_uniforms,
+                                    int row0, const uint32_t* d_halo_top,
+                                    const uint32_t* d_halo_bot, uintptr_t stream);
+/* d_out[replica][0] = number of up spins, d_out[replica][1] = number of anti-aligned bonds
+ * (right + down bonds of every local site, wiring of tsu/models/ising.py:343-361).
+ * d_next_rows: [n_replicas][2][wpr] both colours of global row row0+rows (slab sharding) or NULL.
+ * M and E follow on the host: M = (2 up - N)/N, E = -J (n_bonds - 2 anti) - h (2 up - N)
+ * (tsu/models/ising.py:98-117,183-193). */
+int tsu_ising2d_observables(const uint32_t* d_state, int n_replicas, int rows, int cols,
+                            int wrap_rows, int wrap_cols, int row0, const uint32_t* d_next_rows,
+                            unsigned long long* d_out, uintptr_t stream);
+/* d_energy[r] = -J (n_bonds - 2 anti_r) - h (2 up_r - n_sites)   (float64) */
+int tsu_ising2d_energy_from_observables(const unsigned long long* d_obs, int n_replicas, double J,
+                                        double h, int64_t n_bonds, int64_t n_sites,
+                                        double* d_energy, uintptr_t stream);
+
+/* ------------------------------------------------------------------ dense-J Gibbs ----- */
+/*
+ * Replaces GibbsSampler.gibbs_sweep / sample_boltzmann / compute_energy and the sweep part of
+ * parallel_tempering / simulated_annealing (tsu/gibbs.py:128-236,284-303,370-391) for a batch
+ * of independent chains sharing one coupling matrix.
+ *   d_Jt: [N][N] row-major TRANSPOSE of the coupling matrix, Jt[i*N+j] = J[j][i] (the same array as
+ *     J when J is symmetric; the reference allows asymmetric J, gibbs.py:117); j_dtype 0 = float32,
+ *     1 = float64;  d_bias: [N] same dtype or NULL.
+ *   d_state: [n_chains][N] uint8 bits, updated in place.
+ *   Local field includes the self term J_ii s_i (tsu/gibbs.py:97).  Site i of chain c in sweep s
+ *   takes new bit = 1 iff u < sigmoid(h_i / T) (sigmoid clamped at |x| > 20, gibbs.py:73-77).
+ *   Temperature of (chain c, sweep s): d_T_chain ? d_T_chain[c] : (d_T_sweep ? d_T_sweep[s] : T).
+ *   d_order: [n_total_sweeps][V] int32 visiting order (NULL = 0..N-1, "sequential"); V =
+ *     visits_per_sweep (0 means N; V < N gives partial sweeps, e.g. one sample_conditional).
+ *   d_uniforms: [n_total_sweeps][n_chains][V] float64 in visiting order (parity mode) or NULL
+ *     (Philox: counter = (site, chain0+chain, sweep0+s, 'DENS')).
+ *   Schedule: n_burnin sweeps, then n_samples x sweeps_per_sample sweeps; after each group the
+ *   state of every chain is written to d_samples[sample][chain][N] (uint8, may be NULL).
+ *   d_energy: [n_chains] float64 energy -1/2 s^T J s - b^T s of the final state (may be NULL).
+ *   track_best: after every sweep keep the lowest-energy state per chain in
+ *     d_best_state[n_chains][N] / d_best_energy[n_chains] (simulated annealing, gibbs.py:387-391).
+ *   acc_dtype: 0 = float32 fields, 1 = float64 fields.
+ */
+int tsu_dense_gibbs_run(const void* d_Jt, int j_dtype, const void* d_bias, uint8_t* d_state,
+                        int n_chains, int N, double T, const double* d_T_chain,
+                        const double* d_T_sweep, int n_burnin, int n_samples,
+                        int sweeps_per_sample, const int32_t* d_order, const double* d_uniforms,
+                        uint8_t* d_samples, double* d_energy, int track_best,
+                        uint8_t* d_best_state, double* d_best_energy, uint64_t seed,
+                        uint32_t sweep0, uint32_t chain0, int acc_dtype, int visits_per_sweep,
+                        uintptr_t stream);
+/* d_energy[c] = -1/2 s^T J s - b^T s   (tsu/gibbs.py:215-236), float64 accumulation */
+int tsu_dense_energy(const void* d_Jt, int j_dtype, const void* d_bias, const uint8_t* d_state,
+                     int n_chains, int N, double* d_energy, uintptr_t stream);
+/* iid Bernoulli(1/2) chain states from Philox ('DINI' stream); np.random.randint(0,2,N) of gibbs.py:201 */
+int tsu_dense_init_random(uint8_t* d_state, int n_chains, int N, uint64_t seed, uint32_t chain0,
+                          uintptr_t stream);
+
+/* Replica-exchange pass (tsu/gibbs.py:308-323): for each ladder, pairs i = 0..R-2 in order;
+ * delta = (1/T_i - 1/T_{i+1}) (E_{i+1} - E_i); accept if delta >= 0 or u < exp(delta) (u drawn
+ * only when delta < 0).  Configurations stay in place; d_slot_replica[ladder][i] (the replica
+ * currently at temperature slot i) is permuted instead, and d_lut_index[replica] (may be NULL)
+ * is updated to the slot for the lattice kernels.  d_stats[0] += attempts, d_stats[1] += accepts.
+ * d_uniforms: [n_ladders][R-1] float64 (parity mode) or NULL (Philox 'PTSW', step). */
+int tsu_pt_swap(const double* d_energy, const double* d_T_slot, int32_t* d_slot_replica,
+                int32_t* d_lut_index, int n_ladders, int R, uint64_t seed, uint32_t step,
+                unsigned long long* d_stats, const double* d_uniforms, uintptr_t stream);
+
+/* ------------------------------------------------------------------ Langevin ---------- */
+/*
+ * Replaces the loop of ThermalSamplingUnit.sample_from_energy (tsu/core.py:100-162) for
+ * built-in analytic energies: every "sample" of the reference is an independent restarted chain
+ * (core.py:140-143), so n_samples chains run in parallel, one per thread, state in registers.
+ *   step (core.py:64-80):  x <- x - grad E(x) dt/gamma + sqrt(2 T dt / gamma) N(0, I)
+ *   chain c starts at x_init (c == 0 and chain0 == 0) or x_init + jitter * N(0, I) (core.py:142-143)
+ *   energy_kind / d_params (float64 device array):
+ *     0 QUADRATIC    E = a * sum_i ((x_i - mu_i)^2 * w_i)         params = [a, mu[dim], w[dim]]
+ *     1 MIXTURE      E = -log(sum_k p_k exp(-|x - c_k|^2 / 2) + 1e-10)   (tsu/api.py:143-149)
+ *                                                                 params = [K, p[K], c[K][dim]]
+ *     2 DOUBLE_WELL  E = sum_i a (x_i^2 - b)^2                    params = [a, b]
+ *   dtype 0 = float32, 1 = float64 for d_x / d_x_init / d_traj / d_normals.
+ *   d_x: [n_chains][dim] final states (the reference's `samples`).
+ *   d_traj: [n_chains][n_steps][dim] sampling-phase trajectory or NULL (core.py:155-156).
+ *   d_normals: [n_chains][1 + n_burnin + n_steps][dim] injected N(0,1) draws (parity mode; row 0
+ *     is the start jitter) or NULL (Philox + Box-Muller, counter = (chain, pair, step, 'LANG')).
+ */
+int tsu_langevin_run(void* d_x, int dtype, int64_t n_chains, int dim, int energy_kind,
+                     const double* d_params, int n_params, const void* d_x_init, double jitter,
+                     double T, double dt, double gamma, int n_burnin, int n_steps, uint64_t seed,
+                     uint64_t chain0, const void* d_normals, void* d_traj, uintptr_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSU_B200_H */

@@ -1,0 +1,68 @@
+// Library-level entry points: version, error strings, device probe, Philox helpers.
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace {
+
+__global__ void philox_fill_kernel(uint32_t* out, uint64_t n, uint32_t k0, uint32_t k1, uint32_t offset) {
+  const uint64_t blk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one Philox block = 4 words
+  const uint64_t base = blk * 4;
+  if (base >= n) return;
+  tsu_u32x4 o = tsu_philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), offset, TSU_STREAM_FILL, k0, k1);
+  out[base] = o.x;
+  if (base + 1 < n) out[base + 1] = o.y;
+  if (base + 2 < n) out[base + 2] = o.z;
+  if (base + 3 < n) out[base + 3] = o.w;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tsu_version(void) { return TSU_B200_ABI_VERSION; }
+
+const char* tsu_error_string(int code) {
+  if (code == TSU_OK) return "ok";
+  if (code == TSU_ERR_INVALID_ARG) return "invalid argument";
+  if (code == TSU_ERR_UNSUPPORTED) return "unsupported configuration";
+  if (code == TSU_ERR_NO_DEVICE) return "no CUDA device";
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "unknown error";
+}
+
+int tsu_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return TSU_ERR_NO_DEVICE;
+  }
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  cudaDeviceProp p;
+  e = cudaGetDeviceProperties(&p, dev);
+  if (e != cudaSuccess) return (int)e;
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return TSU_OK;
+}
+
+void tsu_philox4x32_10_host(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  tsu_u32x4 o = tsu_philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+  out[0] = o.x;
+  out[1] = o.y;
+  out[2] = o.z;
+  out[3] = o.w;
+}
+
+int tsu_philox_fill_u32(uint32_t* d_out, uint64_t n, uint64_t seed, uint32_t offset, uintptr_t stream) {
+  TSU_CHECK_ARG(d_out || n == 0);
+  if (n == 0) return TSU_OK;
+  const uint64_t blocks4 = (n + 3) / 4;
+  const unsigned grid = (unsigned)((blocks4 + 255) / 256);
+  philox_fill_kernel<<<grid, 256, 0, tsu_stream(stream)>>>(d_out, n, (uint32_t)seed, (uint32_t)(seed >> 32), offset);
+  TSU_RETURN_LAUNCH_STATUS();
+}
+
+}  // extern "C"

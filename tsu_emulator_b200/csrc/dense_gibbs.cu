@@ -1,0 +1,381 @@
+// Dense-coupling heat-bath Gibbs sampler: exact sequential single-site updates, one CTA per chain,
+// incrementally maintained local fields (sm_100a).
+//
+// Replaces the hot loop of the reference
+//   GibbsSampler.gibbs_sweep / sample_conditional / _compute_local_field  tsu/gibbs.py:79-162
+//   GibbsSampler.sample_boltzmann (burn-in + n_samples x n_sweeps)        tsu/gibbs.py:164-213
+//   GibbsSampler.compute_energy                                           tsu/gibbs.py:215-236
+// for a batch of independent chains that share one coupling matrix (the "parallel chains" that
+// HardwareEmulator.sample_parallel, gibbs.py:450-487, and parallel_tempering, gibbs.py:284-303,
+// run one after the other).
+//
+// The reference recomputes h_i = J[i,:] . s + b_i (O(N)) for every visited site.  Here every chain
+// keeps all N local fields in shared memory; a site visit is O(1) (read h_i, sigmoid, compare) and
+// only an actual flip costs O(N): h_j += J[j,i] * (new - old) for all j, one coalesced row of the
+// transposed coupling matrix read from L2.  The self term J_ii s_i stays part of h_i exactly as in
+// gibbs.py:97.  One __syncthreads per visited site: writes to h_i / s_i of the site just decided
+// are deferred by one step so that slow readers of the same step never race with them.
+
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace {
+
+struct DenseParams {
+  const void* Jt;  // [N][N] row-major transpose of J: Jt[i*N + j] = J[j][i]
+  const void* bias;
+  uint8_t* state;
+  const double* T_chain;
+  const double* T_sweep;
+  const int32_t* order;
+  const double* uniforms;
+  uint8_t* samples;
+  double* energy;
+  uint8_t* best_state;
+  double* best_energy;
+  double T;
+  int n_chains, N;
+  int n_visit;  // sites visited per sweep (N for a full sweep)
+  int n_burnin, n_samples, sweeps_per_sample;
+  int track_best;
+  int refresh_every;  // recompute fields from scratch every this many sweeps (float32 fields)
+  uint32_t k0, k1, sweep0, chain0;
+};
+
+template <typename AT>
+__device__ __forceinline__ AT sigmoid_clamped(AT x);
+
+// tsu/gibbs.py:61-77: x > 20 -> 1, x < -20 -> 0 (strict), else 1 / (1 + exp(-x))
+template <>
+__device__ __forceinline__ double sigmoid_clamped<double>(double x) {
+  if (x > 20.0) return 1.0;
+  if (x < -20.0) return 0.0;
+  return 1.0 / (1.0 + exp(-x));
+}
+template <>
+__device__ __forceinline__ float sigmoid_clamped<float>(float x) {
+  if (x > 20.0f) return 1.0f;
+  if (x < -20.0f) return 0.0f;
+  return 1.0f / (1.0f + expf(-x));
+}
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < nw; ++w) t += red[w];  // same order in every thread: deterministic
+  return t;
+}
+
+template <typename JT, typename AT>
+__device__ void compute_fields(const DenseParams& P, const uint8_t* s, AT* h) {
+  const JT* Jt = reinterpret_cast<const JT*>(P.Jt);
+  const JT* b = reinterpret_cast<const JT*>(P.bias);
+  const int N = P.N;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    AT acc = (AT)0;
+    for (int k = 0; k < N; ++k)
+      if (s[k]) acc += (AT)Jt[(size_t)k * N + j];  // h_j = sum_k J[j][k] s_k  (ascending k)
+    if (b) acc += (AT)b[j];
+    h[j] = acc;
+  }
+}
+
+// E = -1/2 s^T J s - b^T s = -1/2 sum_i s_i h_i - 1/2 sum_i b_i s_i   (h includes the bias)
+template <typename JT, typename AT>
+__device__ double chain_energy(const DenseParams& P, const uint8_t* s, const AT* h, double* red) {
+  const JT* b = reinterpret_cast<const JT*>(P.bias);
+  double acc = 0.0;
+  for (int j = threadIdx.x; j < P.N; j += blockDim.x)
+    if (s[j]) acc += -0.5 * (double)h[j] - (b ? 0.5 * (double)b[j] : 0.0);
+  return block_sum(acc, red);
+}
+
+template <typename JT, typename AT>
+__global__ void dense_gibbs_kernel(DenseParams P) {
+  extern __shared__ double smem_d[];
+  const int N = P.N;
+  double* u = smem_d;                                   // [N] uniforms of the current sweep (visit order)
+  double* red = u + N;                                  // [32]
+  AT* h = reinterpret_cast<AT*>(red + 32);              // [N] local fields
+  uint8_t* s = reinterpret_cast<uint8_t*>(h + N);       // [N] bits
+  const int chain = blockIdx.x;
+  const JT* Jt = reinterpret_cast<const JT*>(P.Jt);
+  uint8_t* gstate = P.state + (size_t)chain * N;
+
+  for (int j = threadIdx.x; j < N; j += blockDim.x) s[j] = gstate[j] ? 1 : 0;
+  __syncthreads();
+  compute_fields<JT, AT>(P, s, h);
+  __syncthreads();
+
+  double best_e = 0.0;
+  if (P.track_best) {
+    best_e = chain_energy<JT, AT>(P, s, h, red);
+    for (int j = threadIdx.x; j < N; j += blockDim.x) P.best_state[(size_t)chain * N + j] = s[j];
+  }
+
+  const int total = P.n_burnin + P.n_samples * P.sweeps_per_sample;
+  int next_sample_at = P.n_burnin + P.sweeps_per_sample;
+  int sample_idx = 0;
+  for (int sw = 0; sw < total; ++sw) {
+    const double Td = P.T_chain ? P.T_chain[chain] : (P.T_sweep ? P.T_sweep[sw] : P.T);
+    const AT T = (AT)Td;
+    if (P.refresh_every > 0 && sw > 0 && (sw % P.refresh_every) == 0) {
+      compute_fields<JT, AT>(P, s, h);
+    }
+    const int NV = P.n_visit;
+    const int32_t* ord = P.order ? P.order + (size_t)sw * NV : nullptr;
+    // uniforms of this sweep, in visiting order
+    for (int idx = threadIdx.x; idx < NV; idx += blockDim.x) {
+      if (P.uniforms) {
+        u[idx] = P.uniforms[((size_t)sw * P.n_chains + chain) * NV + idx];
+      } else {
+        const int site = ord ? ord[idx] : idx;
+        tsu_u32x4 o = tsu_philox4x32_10((uint32_t)site, P.chain0 + (uint32_t)chain, P.sweep0 + (uint32_t)sw,
+                                        TSU_STREAM_DENSE, P.k0, P.k1);
+        const unsigned long long m = (((unsigned long long)o.x << 32) | o.y) >> 11;
+        u[idx] = (double)m * (1.0 / 9007199254740992.0);
+      }
+    }
+    __syncthreads();
+
+    int pend_i = -1;       // site decided in the previous step: its s / self-term writes are deferred
+    int pend_bit = 0;
+    AT pend_delta = (AT)0;
+    for (int idx = 0; idx < NV; ++idx) {
+      const int i = ord ? ord[idx] : idx;
+      const AT hi = h[i];
+      const int si = s[i];
+      const double ui = u[idx];
+      // deferred writes of the previous step (all threads have finished reading that site)
+      if (pend_i >= 0) {
+        if (threadIdx.x == (pend_i % blockDim.x)) {
+          s[pend_i] = (uint8_t)pend_bit;
+          if (pend_delta != (AT)0) h[pend_i] += (AT)Jt[(size_t)pend_i * N + pend_i] * pend_delta;
+        }
+      }
+      const AT p = sigmoid_clamped<AT>(hi / T);          // gibbs.py:124-125
+      const int nb = (ui < (double)p) ? 1 : 0;           // gibbs.py:126 (strict <)
+      const AT delta = (AT)(nb - si);
+      if (delta != (AT)0) {
+        const JT* row = Jt + (size_t)i * N;               // column i of J
+        for (int j = threadIdx.x; j < N; j += blockDim.x)
+          if (j != i) h[j] += (AT)row[j] * delta;
+      }
+      pend_i = i;
+      pend_bit = nb;
+      pend_delta = delta;
+      __syncthreads();
+    }
+    if (pend_i >= 0 && threadIdx.x == (pend_i % blockDim.x)) {
+      s[pend_i] = (uint8_t)pend_bit;
+      if (pend_delta != (AT)0) h[pend_i] += (AT)Jt[(size_t)pend_i * N + pend_i] * pend_delta;
+    }
+    __syncthreads();
+
+    if (P.track_best) {  // gibbs.py:387-391
+      const double e = chain_energy<JT, AT>(P, s, h, red);
+      if (e < best_e) {
+        best_e = e;
+        for (int j = threadIdx.x; j < N; j += blockDim.x) P.best_state[(size_t)chain * N + j] = s[j];
+      }
+    }
+    if (P.samples && sw + 1 == next_sample_at && sample_idx < P.n_samples) {
+      uint8_t* dst = P.samples + ((size_t)sample_idx * P.n_chains + chain) * N;
+      for (int j = threadIdx.x; j < N; j += blockDim.x) dst[j] = s[j];
+      ++sample_idx;
+      next_sample_at += P.sweeps_per_sample;
+    } else if (sw + 1 == next_sample_at) {
+      ++sample_idx;
+      next_sample_at += P.sweeps_per_sample;
+    }
+  }
+  for (int j = threadIdx.x; j < N; j += blockDim.x) gstate[j] = s[j];
+  if (P.energy) {
+    const double e = chain_energy<JT, AT>(P, s, h, red);
+    if (threadIdx.x == 0) P.energy[chain] = e;
+  }
+  if (P.track_best && threadIdx.x == 0) P.best_energy[chain] = best_e;
+}
+
+// E = -1/2 s^T J s - b^T s from scratch, float64 accumulation (tsu/gibbs.py:215-236)
+template <typename JT>
+__global__ void dense_energy_kernel(const JT* __restrict__ Jt, const JT* __restrict__ bias,
+                                    const uint8_t* __restrict__ state, int N, double* energy) {
+  __shared__ double red[32];
+  const int chain = blockIdx.x;
+  const uint8_t* s = state + (size_t)chain * N;
+  double acc = 0.0;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    if (!s[j]) continue;
+    double hj = 0.0;
+    for (int k = 0; k < N; ++k)
+      if (s[k]) hj += (double)Jt[(size_t)k * N + j];
+    acc += -0.5 * hj - (bias ? (double)bias[j] : 0.0);
+  }
+  const double e = block_sum(acc, red);
+  if (threadIdx.x == 0) energy[chain] = e;
+}
+
+__global__ void dense_init_kernel(uint8_t* state, int n_chains, int N, uint32_t k0, uint32_t k1, uint32_t chain0) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 32 sites
+  const int wpc = (N + 31) / 32;
+  if (t >= (long long)n_chains * wpc) return;
+  const int chain = (int)(t / wpc);
+  const int w = (int)(t - (long long)chain * wpc);
+  tsu_u32x4 o = tsu_philox4x32_10((uint32_t)w, chain0 + (uint32_t)chain, 0u, TSU_STREAM_DENSE_INIT, k0, k1);
+  for (int b = 0; b < 32; ++b) {
+    const int i = 32 * w + b;
+    if (i < N) state[(size_t)chain * N + i] = (uint8_t)((o.x >> b) & 1u);
+  }
+}
+
+// One thread per ladder walks the pairs in order (gibbs.py:308-323).
+__global__ void pt_swap_kernel(const double* __restrict__ energy, const double* __restrict__ T_slot,
+                               int32_t* slot_replica, int32_t* lut_index, int n_ladders, int R, uint32_t k0,
+                               uint32_t k1, uint32_t step, unsigned long long* stats,
+                               const double* __restrict__ uniforms) {
+  const int ladder = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ladder >= n_ladders) return;
+  int32_t* sr = slot_replica + (size_t)ladder * R;
+  unsigned long long attempts = 0, accepts = 0;
+  for (int i = 0; i + 1 < R; ++i) {
+    const int ra = sr[i], rb = sr[i + 1];
+    const double Ei = energy[ra], Ej = energy[rb];
+    const double delta = (1.0 / T_slot[i] - 1.0 / T_slot[i + 1]) * (Ej - Ei);
+    ++attempts;
+    bool acc = delta >= 0.0;
+    if (!acc) {  // the uniform is consumed only when delta < 0 (short-circuit `or`, gibbs.py:320)
+      double uu;
+      if (uniforms) {
+        uu = uniforms[(size_t)ladder * (R - 1) + i];
+      } else {
+        tsu_u32x4 o = tsu_philox4x32_10((uint32_t)i, (uint32_t)ladder, step, TSU_STREAM_PT_SWAP, k0, k1);
+        const unsigned long long m = (((unsigned long long)o.x << 32) | o.y) >> 11;
+        uu = (double)m * (1.0 / 9007199254740992.0);
+      }
+      acc = uu < exp(delta);
+    }
+    if (acc) {
+      sr[i] = rb;
+      sr[i + 1] = ra;
+      ++accepts;
+    }
+  }
+  if (lut_index)
+    for (int i = 0; i < R; ++i) lut_index[sr[i]] = i;
+  if (stats) {
+    atomicAdd(stats, attempts);
+    atomicAdd(stats + 1, accepts);
+  }
+}
+
+int pick_threads(int N) {
+  int t = (N + 15) / 16;        // about 16 fields per thread
+  t = (t + 31) / 32 * 32;
+  if (t < 32) t = 32;
+  if (t > 512) t = 512;
+  return t;
+}
+
+template <typename JT, typename AT>
+int launch_dense(const DenseParams& P, cudaStream_t st) {
+  const size_t smem = sizeof(double) * ((size_t)P.N + 32) + sizeof(AT) * (size_t)P.N + (size_t)P.N + 16;
+  if (smem > 227 * 1024) return TSU_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e =
+        cudaFuncSetAttribute(dense_gibbs_kernel<JT, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  dense_gibbs_kernel<JT, AT><<<P.n_chains, pick_threads(P.N), smem, st>>>(P);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? TSU_OK : (int)e;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tsu_dense_gibbs_run(const void* d_Jt, int j_dtype, const void* d_bias, uint8_t* d_state, int n_chains, int N,
+                        double T, const double* d_T_chain, const double* d_T_sweep, int n_burnin, int n_samples,
+                        int sweeps_per_sample, const int32_t* d_order, const double* d_uniforms, uint8_t* d_samples,
+                        double* d_energy, int track_best, uint8_t* d_best_state, double* d_best_energy, uint64_t seed,
+                        uint32_t sweep0, uint32_t chain0, int acc_dtype, int visits_per_sweep, uintptr_t stream) {
+  TSU_CHECK_ARG(d_Jt && d_state && n_chains > 0 && N > 0);
+  TSU_CHECK_ARG(visits_per_sweep >= 0 && visits_per_sweep <= N && (visits_per_sweep == 0 || d_order));
+  TSU_CHECK_ARG(j_dtype == 0 || j_dtype == 1);
+  TSU_CHECK_ARG(acc_dtype == 0 || acc_dtype == 1);
+  TSU_CHECK_ARG(n_burnin >= 0 && n_samples >= 0 && sweeps_per_sample >= 0);
+  TSU_CHECK_ARG(n_samples == 0 || sweeps_per_sample > 0);
+  TSU_CHECK_ARG(d_T_chain || d_T_sweep || T > 0);
+  TSU_CHECK_ARG(!track_best || (d_best_state && d_best_energy));
+  DenseParams P;
+  P.Jt = d_Jt;
+  P.bias = d_bias;
+  P.state = d_state;
+  P.T_chain = d_T_chain;
+  P.T_sweep = d_T_sweep;
+  P.order = d_order;
+  P.uniforms = d_uniforms;
+  P.samples = d_samples;
+  P.energy = d_energy;
+  P.best_state = d_best_state;
+  P.best_energy = d_best_energy;
+  P.T = T;
+  P.n_chains = n_chains;
+  P.N = N;
+  P.n_visit = visits_per_sweep > 0 ? visits_per_sweep : N;
+  P.n_burnin = n_burnin;
+  P.n_samples = n_samples;
+  P.sweeps_per_sample = sweeps_per_sample;
+  P.track_best = track_best;
+  P.refresh_every = acc_dtype == 0 ? 8 : 0;
+  P.k0 = (uint32_t)seed;
+  P.k1 = (uint32_t)(seed >> 32);
+  P.sweep0 = sweep0;
+  P.chain0 = chain0;
+  cudaStream_t st = tsu_stream(stream);
+  if (j_dtype == 0 && acc_dtype == 0) return launch_dense<float, float>(P, st);
+  if (j_dtype == 0 && acc_dtype == 1) return launch_dense<float, double>(P, st);
+  if (j_dtype == 1 && acc_dtype == 0) return launch_dense<double, float>(P, st);
+  return launch_dense<double, double>(P, st);
+}
+
+int tsu_dense_energy(const void* d_Jt, int j_dtype, const void* d_bias, const uint8_t* d_state, int n_chains, int N,
+                     double* d_energy, uintptr_t stream) {
+  TSU_CHECK_ARG(d_Jt && d_state && d_energy && n_chains > 0 && N > 0);
+  TSU_CHECK_ARG(j_dtype == 0 || j_dtype == 1);
+  const int threads = pick_threads(N);
+  if (j_dtype == 0)
+    dense_energy_kernel<float><<<n_chains, threads, 0, tsu_stream(stream)>>>(
+        reinterpret_cast<const float*>(d_Jt), reinterpret_cast<const float*>(d_bias), d_state, N, d_energy);
+  else
+    dense_energy_kernel<double><<<n_chains, threads, 0, tsu_stream(stream)>>>(
+        reinterpret_cast<const double*>(d_Jt), reinterpret_cast<const double*>(d_bias), d_state, N, d_energy);
+  TSU_RETURN_LAUNCH_STATUS();
+}
+
+int tsu_dense_init_random(uint8_t* d_state, int n_chains, int N, uint64_t seed, uint32_t chain0, uintptr_t stream) {
+  TSU_CHECK_ARG(d_state && n_chains > 0 && N > 0);
+  const long long total = (long long)n_chains * ((N + 31) / 32);
+  dense_init_kernel<<<(unsigned)((total + 127) / 128), 128, 0, tsu_stream(stream)>>>(
+      d_state, n_chains, N, (uint32_t)seed, (uint32_t)(seed >> 32), chain0);
+  TSU_RETURN_LAUNCH_STATUS();
+}
+
+int tsu_pt_swap(const double* d_energy, const double* d_T_slot, int32_t* d_slot_replica, int32_t* d_lut_index,
+                int n_ladders, int R, uint64_t seed, uint32_t step, unsigned long long* d_stats,
+                const double* d_uniforms, uintptr_t stream) {
+  TSU_CHECK_ARG(d_energy && d_T_slot && d_slot_replica && n_ladders > 0 && R > 0);
+  pt_swap_kernel<<<(n_ladders + 63) / 64, 64, 0, tsu_stream(stream)>>>(d_energy, d_T_slot, d_slot_replica,
+                                                                      d_lut_index, n_ladders, R, (uint32_t)seed,
+                                                                      (uint32_t)(seed >> 32), step, d_stats,
+                                                                      d_uniforms);
+  TSU_RETURN_LAUNCH_STATUS();
+}
+
+}  // extern "C"

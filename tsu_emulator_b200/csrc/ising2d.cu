@@ -1,0 +1,660 @@
+// 2-D nearest-neighbour Ising lattice: bit-packed checkerboard heat-bath Gibbs update for sm_100a.
+//
+// Replaces the per-spin Python loop of the reference
+//   GibbsSampler.gibbs_sweep / sample_conditional   tsu/gibbs.py:102-162
+// for the lattice wired by IsingGrid                 tsu/models/ising.py:320-361
+// (and README's IsingModel2D.gibbs_update, README.md:116-131).
+//
+// Multi-spin coding: one uint32 word = 32 spins of one colour of one row.  For a word the four
+// neighbour words (north, south, centre, side-shifted) are reduced to a bit-sliced up-count
+// (c2 c1 c0) with 6 LOP3 + 1 funnel shift.  The acceptance test  u < t[class]  (u: 32-bit uniform
+// per spin, t: integer threshold = ceil(sigmoid(h/T) * 2^32) from the host LUT) is evaluated
+// bit-sliced as well: the top 8 bits of all 32 uniforms are 8 random bit-planes = 2 Philox calls;
+// a borrow chain gives "less than" and "equal so far" masks.  Only lanes whose top 8 bits tie with
+// the threshold (probability 2^-8) need the low 24 bits, which come from a per-lane-group Philox
+// call.  The result is identical to a full 32-bit compare per spin, so it is bit-exact with the
+// CPU oracle (oracle/ising2d_oracle.py) and with the reference's `rand() < prob`.
+//
+// HBM traffic per half-sweep: read the opposite colour once (+2 halo rows per strip), write the
+// updated colour once = 2 bits per spin update; the kernel is integer-issue bound, not DRAM bound
+// (see DESIGN.md for the roofline arithmetic).
+
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace {
+
+struct Geom {
+  int rows, cols, wpr;
+  int wrap_rows, wrap_cols;
+  int row0;
+  int n_replicas;
+};
+
+__host__ __device__ __forceinline__ int colour_count(int cols, int p) { return (cols - p + 1) >> 1; }
+
+__host__ __device__ __forceinline__ int words_per_row(int cols) {
+  int ck = (cols + 1) / 2;
+  int w = (ck + 31) / 32;
+  return (w + 3) / 4 * 4;
+}
+
+__device__ __forceinline__ uint32_t lane_mask_lt(int n) {  // lanes [0, n), n clamped to [0, 32]
+  return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u));
+}
+
+// pointers to the two colour planes of one replica
+struct Planes {
+  const uint32_t* opp;       // plane of the colour NOT being updated: [rows][wpr]
+  const uint32_t* halo_top;  // opposite-colour row above local row 0, or nullptr
+  const uint32_t* halo_bot;  // opposite-colour row below local row rows-1, or nullptr
+};
+
+__device__ __forceinline__ const uint32_t* opp_row(const Planes& P, const Geom& g, int i) {
+  if (i < 0) return P.halo_top ? P.halo_top : (g.wrap_rows ? P.opp + (size_t)(g.rows - 1) * g.wpr : nullptr);
+  if (i >= g.rows) return P.halo_bot ? P.halo_bot : (g.wrap_rows ? P.opp : nullptr);
+  return P.opp + (size_t)i * g.wpr;
+}
+
+// Neighbourhood of word w of (colour, local row i) with all boundary cases.
+struct Hood {
+  uint32_t n, s, c, side;  // neighbour bit words (missing neighbours read 0)
+  uint32_t valid;          // own lanes that exist
+  uint32_t missW, missE;   // own lanes without a west / east neighbour (open columns)
+  int has_n, has_s;
+};
+
+__device__ __forceinline__ Hood load_hood(const Planes& P, const Geom& g, int colour, int i, int w) {
+  Hood h;
+  const int p = (g.row0 + i + colour) & 1;  // column offset of the own colour in this row
+  const int nk_own = colour_count(g.cols, p);
+  const int nk_opp = colour_count(g.cols, 1 - p);
+  h.valid = lane_mask_lt(nk_own - 32 * w);
+  const uint32_t* rn = opp_row(P, g, i - 1);
+  const uint32_t* rs = opp_row(P, g, i + 1);
+  const uint32_t* rc = P.opp + (size_t)i * g.wpr;
+  h.has_n = rn != nullptr;
+  h.has_s = rs != nullptr;
+  h.n = rn ? rn[w] : 0u;
+  h.s = rs ? rs[w] : 0u;
+  h.c = rc[w];
+  h.missW = 0u;
+  h.missE = 0u;
+  const int last = nk_own - 1;  // last own lane index in the row
+  if (p) {
+    // own col = 2k+1: west = opp k (centre), east = opp k+1
+    uint32_t nx = (w + 1 < g.wpr) ? rc[w + 1] : 0u;
+    h.side = (h.c >> 1) | (nx << 31);
+    if (last >= 0 && (last >> 5) == w && 2 * last + 2 >= g.cols) {  // east neighbour would be col >= cols
+      if (g.wrap_cols)
+        h.side |= (rc[0] & 1u) << (last & 31);
+      else
+        h.missE = 1u << (last & 31);
+    }
+  } else {
+    // own col = 2k: east = opp k (centre), west = opp k-1
+    uint32_t pv = (w > 0) ? rc[w - 1] : 0u;
+    h.side = (h.c << 1) | (pv >> 31);
+    if (w == 0) {
+      if (g.wrap_cols) {
+        int lo = nk_opp - 1;
+        h.side |= (rc[lo >> 5] >> (lo & 31)) & 1u;
+      } else {
+        h.missW = 1u;
+      }
+    }
+    if (last >= 0 && (last >> 5) == w && 2 * last + 1 >= g.cols) h.missE = 1u << (last & 31);  // odd cols
+  }
+  return h;
+}
+
+// ---- bit-sliced acceptance -------------------------------------------------------------
+struct LutRegs {
+  uint32_t K[8][5];  // K[k][u] = all-ones iff bit (31-k) of threshold(d, u) is set
+  uint32_t always;   // bit u set: class (d, u) accepts with probability 1 (threshold 2^32)
+};
+
+__device__ __forceinline__ void load_lut_regs(LutRegs& L, const uint32_t* __restrict__ lut, int d) {
+#pragma unroll
+  for (int u = 0; u < 5; ++u) {
+    uint32_t t = __ldg(lut + d * 5 + u);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) L.K[k][u] = 0u - ((t >> (31 - k)) & 1u);
+  }
+  L.always = (__ldg(lut + 25) >> (d * 5)) & 31u;
+}
+
+__device__ __forceinline__ uint32_t bitsel(uint32_t m, uint32_t a, uint32_t b) {  // m ? a : b  (bitwise)
+  return (m & a) | (~m & b);
+}
+
+struct Coords {
+  uint32_t c0_base;  // w | colour << 20   (kind added per call)
+  uint32_t row_g, sweep, replica, k0, k1;
+};
+
+__device__ __forceinline__ tsu_u32x4 lattice_call(const Coords& q, uint32_t kind) {
+  return tsu_philox4x32_10(q.c0_base | (kind << 21), q.row_g, q.sweep, q.replica, q.k0, q.k1);
+}
+
+// full 32-bit uniform of lane j (top 8 bits from the planes, low 24 bits from the lane-group call)
+__device__ __forceinline__ uint32_t lane_uniform(const uint32_t r[8], const Coords& q, int j) {
+  uint32_t u = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) u |= ((r[k] >> j) & 1u) << (31 - k);
+  tsu_u32x4 lo = lattice_call(q, TSU_KIND_LOW0 + (uint32_t)(j >> 2));
+  int sel = j & 3;
+  uint32_t v = sel == 0 ? lo.x : (sel == 1 ? lo.y : (sel == 2 ? lo.z : lo.w));
+  return u | (v >> 8);
+}
+
+__device__ __forceinline__ uint32_t lane_accept(const uint32_t* __restrict__ lut, int d, int up, uint32_t u) {
+  int cls = d * 5 + up;
+  if ((__ldg(lut + 25) >> cls) & 1u) return 1u;
+  return u < __ldg(lut + cls) ? 1u : 0u;
+}
+
+// New value of one word of the colour being updated.
+//   a,b,c,s: neighbour words; d_row: number of neighbours of a regular lane (2 + has_n + has_s);
+//   special: lanes with fewer neighbours than d_row (missW | missE), resolved one by one.
+template <bool FAST>
+__device__ __forceinline__ uint32_t update_word(uint32_t a, uint32_t b, uint32_t c, uint32_t s, const LutRegs& L,
+                                                const uint32_t* __restrict__ lut, int d_row, uint32_t valid,
+                                                uint32_t missW, uint32_t missE, const Coords& q) {
+  // bit-sliced count of up neighbours: c2 c1 c0
+  const uint32_t s1 = a ^ b ^ c;
+  const uint32_t m1 = tsu_lop3_maj(a, b, c);
+  const uint32_t c0 = s1 ^ s;
+  const uint32_t k2 = s1 & s;
+  const uint32_t c1 = m1 ^ k2;
+  const uint32_t c2 = m1 & k2;
+
+  uint32_t r[8];
+  {
+    tsu_u32x4 p0 = lattice_call(q, TSU_KIND_PLANE0);
+    tsu_u32x4 p1 = lattice_call(q, TSU_KIND_PLANE1);
+    r[0] = p0.x; r[1] = p0.y; r[2] = p0.z; r[3] = p0.w;
+    r[4] = p1.x; r[5] = p1.y; r[6] = p1.z; r[7] = p1.w;
+  }
+  uint32_t lt = 0u, eq = 0xffffffffu;
+#pragma unroll
+  for (int k = 7; k >= 0; --k) {  // least significant of the 8 planes first
+    const uint32_t tk = bitsel(c2, L.K[k][4], bitsel(c1, bitsel(c0, L.K[k][3], L.K[k][2]), bitsel(c0, L.K[k][1], L.K[k][0])));
+    const uint32_t x = r[k] ^ tk;
+    lt = (~r[k] & tk) | (~x & lt);
+    eq &= ~x;
+  }
+  const uint32_t always = L.always;
+  if (always) {  // classes with p == 1.0 (threshold 2^32 does not fit 32 bits)
+    uint32_t am = 0u;
+    if (always & 1u) am |= ~c2 & ~c1 & ~c0;
+    if (always & 2u) am |= ~c2 & ~c1 & c0;
+    if (always & 4u) am |= ~c2 & c1 & ~c0;
+    if (always & 8u) am |= ~c2 & c1 & c0;
+    if (always & 16u) am |= c2;
+    lt |= am;
+    eq &= ~am;
+  }
+  uint32_t special = 0u;
+  if (!FAST) {
+    special = (missW | missE) & valid;
+    eq &= valid & ~special;
+  }
+  // lanes whose top 8 bits tie with the threshold: decide on the full 32-bit uniform
+  while (eq) {
+    const int j = __ffs(eq) - 1;
+    eq &= eq - 1u;
+    const int up = ((c0 >> j) & 1u) | (((c1 >> j) & 1u) << 1) | (((c2 >> j) & 1u) << 2);
+    const uint32_t bit = lane_accept(lut, d_row, up, lane_uniform(r, q, j));
+    lt = (lt & ~(1u << j)) | (bit << j);
+  }
+  if (!FAST) {
+    while (special) {
+      const int j = __ffs(special) - 1;
+      special &= special - 1u;
+      const int up = ((c0 >> j) & 1u) | (((c1 >> j) & 1u) << 1) | (((c2 >> j) & 1u) << 2);
+      const int d = d_row - (int)((missW >> j) & 1u) - (int)((missE >> j) & 1u);
+      const uint32_t bit = lane_accept(lut, d, up, lane_uniform(r, q, j));
+      lt = (lt & ~(1u << j)) | (bit << j);
+    }
+    lt &= valid;
+  }
+  return lt;
+}
+
+struct SweepParams {
+  uint32_t* state;
+  const uint32_t* lut;
+  const int32_t* lut_index;
+  const uint32_t* halo_top;
+  const uint32_t* halo_bot;
+  Geom g;
+  int colour;
+  uint32_t sweep, replica0, k0, k1;
+  int strip_rows;  // rows per thread strip (fast path)
+  int n_strips;    // strips per replica (fast path)
+};
+
+// FAST path: periodic columns, every word full (cols % 256 == 0), a neighbour row exists above and
+// below every local row (wrap or halo).  One thread owns a 4-word (128 spin) column strip of
+// `strip_rows` rows and keeps a rolling window (north, centre, south) of 128-bit loads.
+__global__ void __launch_bounds__(128) half_sweep_fast_kernel(SweepParams P) {
+  const Geom& g = P.g;
+  const int nvec = g.wpr >> 2;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_rep = (long long)P.n_strips * nvec;
+  const long long total = per_rep * g.n_replicas;
+  if (tid >= total) return;
+  const int rep = (int)(tid / per_rep);
+  const int rem = (int)(tid - (long long)rep * per_rep);
+  const int strip = rem / nvec;
+  const int v = rem - strip * nvec;
+  const int r_begin = strip * P.strip_rows;
+  const int r_end = min(g.rows, r_begin + P.strip_rows);
+
+  const size_t plane = (size_t)g.rows * g.wpr;
+  uint32_t* own = P.state + ((size_t)rep * 2 + P.colour) * plane;
+  Planes pl;
+  pl.opp = P.state + ((size_t)rep * 2 + (1 - P.colour)) * plane;
+  pl.halo_top = P.halo_top ? P.halo_top + (size_t)rep * g.wpr : nullptr;
+  pl.halo_bot = P.halo_bot ? P.halo_bot + (size_t)rep * g.wpr : nullptr;
+  const uint32_t* lut = P.lut + (P.lut_index ? (size_t)P.lut_index[rep] * 32 : 0);
+
+  LutRegs L;
+  load_lut_regs(L, lut, 4);
+
+  Coords q;
+  q.sweep = P.sweep;
+  q.replica = P.replica0 + (uint32_t)rep;
+  q.k0 = P.k0;
+  q.k1 = P.k1;
+
+  const int w0 = v * 4;
+  const int w_prev = (w0 == 0) ? g.wpr - 1 : w0 - 1;
+  const int w_next = (w0 + 4 == g.wpr) ? 0 : w0 + 4;
+
+  uint4 n = *reinterpret_cast<const uint4*>(opp_row(pl, g, r_begin - 1) + w0);
+  uint4 c = *reinterpret_cast<const uint4*>(opp_row(pl, g, r_begin) + w0);
+  for (int i = r_begin; i < r_end; ++i) {
+    const uint4 s = *reinterpret_cast<const uint4*>(opp_row(pl, g, i + 1) + w0);
+    const int row_g = g.row0 + i;
+    const int p = (row_g + P.colour) & 1;
+    const uint32_t* rc = pl.opp + (size_t)i * g.wpr;
+    uint4 sd;
+    if (p) {
+      const uint32_t nx = rc[w_next];
+      sd.x = __funnelshift_r(c.x, c.y, 1);
+      sd.y = __funnelshift_r(c.y, c.z, 1);
+      sd.z = __funnelshift_r(c.z, c.w, 1);
+      sd.w = __funnelshift_r(c.w, nx, 1);
+    } else {
+      const uint32_t pv = rc[w_prev];
+      sd.x = __funnelshift_l(pv, c.x, 1);
+      sd.y = __funnelshift_l(c.x, c.y, 1);
+      sd.z = __funnelshift_l(c.y, c.z, 1);
+      sd.w = __funnelshift_l(c.z, c.w, 1);
+    }
+    q.row_g = (uint32_t)row_g;
+    uint4 o;
+    q.c0_base = (uint32_t)(w0 + 0) | ((uint32_t)P.colour << 20);
+    o.x = update_word<true>(n.x, s.x, c.x, sd.x, L, lut, 4, 0xffffffffu, 0u, 0u, q);
+    q.c0_base = (uint32_t)(w0 + 1) | ((uint32_t)P.colour << 20);
+    o.y = update_word<true>(n.y, s.y, c.y, sd.y, L, lut, 4, 0xffffffffu, 0u, 0u, q);
+    q.c0_base = (uint32_t)(w0 + 2) | ((uint32_t)P.colour << 20);
+    o.z = update_word<true>(n.z, s.z, c.z, sd.z, L, lut, 4, 0xffffffffu, 0u, 0u, q);
+    q.c0_base = (uint32_t)(w0 + 3) | ((uint32_t)P.colour << 20);
+    o.w = update_word<true>(n.w, s.w, c.w, sd.w, L, lut, 4, 0xffffffffu, 0u, 0u, q);
+    *reinterpret_cast<uint4*>(own + (size_t)i * g.wpr + w0) = o;
+    n = c;
+    c = s;
+  }
+}
+
+// Generic path: any size, open or periodic edges, ragged last word.  One thread per word.
+__global__ void __launch_bounds__(128) half_sweep_generic_kernel(SweepParams P) {
+  const Geom& g = P.g;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_rep = (long long)g.rows * g.wpr;
+  if (tid >= per_rep * g.n_replicas) return;
+  const int rep = (int)(tid / per_rep);
+  const int rem = (int)(tid - (long long)rep * per_rep);
+  const int i = rem / g.wpr;
+  const int w = rem - i * g.wpr;
+
+  const size_t plane = (size_t)g.rows * g.wpr;
+  uint32_t* own = P.state + ((size_t)rep * 2 + P.colour) * plane;
+  Planes pl;
+  pl.opp = P.state + ((size_t)rep * 2 + (1 - P.colour)) * plane;
+  pl.halo_top = P.halo_top ? P.halo_top + (size_t)rep * g.wpr : nullptr;
+  pl.halo_bot = P.halo_bot ? P.halo_bot + (size_t)rep * g.wpr : nullptr;
+  const uint32_t* lut = P.lut + (P.lut_index ? (size_t)P.lut_index[rep] * 32 : 0);
+
+  const Hood h = load_hood(pl, g, P.colour, i, w);
+  if (h.valid == 0u) return;  // padding word (stays 0)
+  const int d_row = 2 + h.has_n + h.has_s;
+  LutRegs L;
+  load_lut_regs(L, lut, d_row);
+  Coords q;
+  q.c0_base = (uint32_t)w | ((uint32_t)P.colour << 20);
+  q.row_g = (uint32_t)(g.row0 + i);
+  q.sweep = P.sweep;
+  q.replica = P.replica0 + (uint32_t)rep;
+  q.k0 = P.k0;
+  q.k1 = P.k1;
+  own[(size_t)i * g.wpr + w] = update_word<false>(h.n, h.s, h.c, h.side, L, lut, d_row, h.valid, h.missW, h.missE, q);
+}
+
+// Parity mode: uniforms injected per site.  One thread per word, one lane at a time.
+__global__ void __launch_bounds__(128) half_sweep_injected_kernel(SweepParams P, const uint32_t* __restrict__ uniforms) {
+  const Geom& g = P.g;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_rep = (long long)g.rows * g.wpr;
+  if (tid >= per_rep * g.n_replicas) return;
+  const int rep = (int)(tid / per_rep);
+  const int rem = (int)(tid - (long long)rep * per_rep);
+  const int i = rem / g.wpr;
+  const int w = rem - i * g.wpr;
+  const size_t plane = (size_t)g.rows * g.wpr;
+  uint32_t* own = P.state + ((size_t)rep * 2 + P.colour) * plane;
+  Planes pl;
+  pl.opp = P.state + ((size_t)rep * 2 + (1 - P.colour)) * plane;
+  pl.halo_top = P.halo_top ? P.halo_top + (size_t)rep * g.wpr : nullptr;
+  pl.halo_bot = P.halo_bot ? P.halo_bot + (size_t)rep * g.wpr : nullptr;
+  const uint32_t* lut = P.lut + (P.lut_index ? (size_t)P.lut_index[rep] * 32 : 0);
+  const Hood h = load_hood(pl, g, P.colour, i, w);
+  if (h.valid == 0u) return;
+  const int p = (g.row0 + i + P.colour) & 1;
+  const uint32_t* urow = uniforms + ((size_t)rep * g.rows + i) * g.cols;
+  uint32_t out = 0u;
+  uint32_t m = h.valid;
+  while (m) {
+    const int j = __ffs(m) - 1;
+    m &= m - 1u;
+    const int up = ((h.n >> j) & 1u) + ((h.s >> j) & 1u) + ((h.c >> j) & 1u) + ((h.side >> j) & 1u);
+    const int d = 2 + h.has_n + h.has_s - (int)((h.missW >> j) & 1u) - (int)((h.missE >> j) & 1u);
+    const int col = 2 * (32 * w + j) + p;
+    out |= lane_accept(lut, d, up, urow[col]) << j;
+  }
+  own[(size_t)i * g.wpr + w] = out;
+}
+
+__global__ void init_random_kernel(uint32_t* state, Geom g, uint32_t replica0, uint32_t k0, uint32_t k1) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_rep = 2LL * g.rows * g.wpr;
+  if (tid >= per_rep * g.n_replicas) return;
+  const int rep = (int)(tid / per_rep);
+  long long rem = tid - (long long)rep * per_rep;
+  const int colour = (int)(rem / ((long long)g.rows * g.wpr));
+  rem -= (long long)colour * g.rows * g.wpr;
+  const int i = (int)(rem / g.wpr);
+  const int w = (int)(rem - (long long)i * g.wpr);
+  const int p = (g.row0 + i + colour) & 1;
+  const uint32_t valid = lane_mask_lt(colour_count(g.cols, p) - 32 * w);
+  tsu_u32x4 o = tsu_philox4x32_10(TSU_LATTICE_C0(w, colour, TSU_KIND_INIT), (uint32_t)(g.row0 + i), 0u,
+                                  replica0 + (uint32_t)rep, k0, k1);
+  state[tid] = o.x & valid;
+}
+
+__global__ void pack_kernel(const int8_t* __restrict__ spins, uint32_t* state, Geom g) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_rep = 2LL * g.rows * g.wpr;
+  if (tid >= per_rep * g.n_replicas) return;
+  const int rep = (int)(tid / per_rep);
+  long long rem = tid - (long long)rep * per_rep;
+  const int colour = (int)(rem / ((long long)g.rows * g.wpr));
+  rem -= (long long)colour * g.rows * g.wpr;
+  const int i = (int)(rem / g.wpr);
+  const int w = (int)(rem - (long long)i * g.wpr);
+  const int p = (g.row0 + i + colour) & 1;
+  const int nk = colour_count(g.cols, p);
+  const int8_t* row = spins + ((size_t)rep * g.rows + i) * g.cols;
+  uint32_t x = 0u;
+  for (int j = 0; j < 32; ++j) {
+    int k = 32 * w + j;
+    if (k < nk && row[2 * k + p] > 0) x |= 1u << j;
+  }
+  state[tid] = x;
+}
+
+__global__ void unpack_kernel(const uint32_t* __restrict__ state, int8_t* spins, Geom g, int as_pm1) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_rep = 2LL * g.rows * g.wpr;
+  if (tid >= per_rep * g.n_replicas) return;
+  const int rep = (int)(tid / per_rep);
+  long long rem = tid - (long long)rep * per_rep;
+  const int colour = (int)(rem / ((long long)g.rows * g.wpr));
+  rem -= (long long)colour * g.rows * g.wpr;
+  const int i = (int)(rem / g.wpr);
+  const int w = (int)(rem - (long long)i * g.wpr);
+  const int p = (g.row0 + i + colour) & 1;
+  const int nk = colour_count(g.cols, p);
+  int8_t* row = spins + ((size_t)rep * g.rows + i) * g.cols;
+  const uint32_t x = state[tid];
+  for (int j = 0; j < 32; ++j) {
+    int k = 32 * w + j;
+    if (k < nk) {
+      int b = (x >> j) & 1u;
+      row[2 * k + p] = (int8_t)(as_pm1 ? 2 * b - 1 : b);
+    }
+  }
+}
+
+// up-spin count and anti-aligned (right + down) bond count per replica
+__global__ void __launch_bounds__(256) observables_kernel(const uint32_t* __restrict__ state, Geom g,
+                                                         const uint32_t* __restrict__ next_rows,
+                                                         unsigned long long* out) {
+  const int rep = blockIdx.y;
+  const size_t plane = (size_t)g.rows * g.wpr;
+  const long long n_words = 2LL * g.rows * g.wpr;
+  unsigned long long ups = 0, anti = 0;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_words;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int colour = (int)(t / ((long long)g.rows * g.wpr));
+    const long long rem = t - (long long)colour * g.rows * g.wpr;
+    const int i = (int)(rem / g.wpr);
+    const int w = (int)(rem - (long long)i * g.wpr);
+    const uint32_t* own = state + ((size_t)rep * 2 + colour) * plane;
+    Planes pl;
+    pl.opp = state + ((size_t)rep * 2 + (1 - colour)) * plane;
+    pl.halo_top = nullptr;
+    pl.halo_bot = next_rows ? next_rows + ((size_t)rep * 2 + (1 - colour)) * g.wpr : nullptr;
+    const Hood h = load_hood(pl, g, colour, i, w);
+    if (h.valid == 0u) continue;
+    const uint32_t x = own[(size_t)i * g.wpr + w];
+    const int p = (g.row0 + i + colour) & 1;
+    ups += __popc(x & h.valid);
+    // east neighbour: centre word if own col is even (p == 0), shifted word otherwise
+    const uint32_t east = p ? h.side : h.c;
+    anti += __popc((x ^ east) & h.valid & ~h.missE);
+    if (h.has_s) anti += __popc((x ^ h.s) & h.valid);
+  }
+  ups = tsu_warp_sum(ups);
+  anti = tsu_warp_sum(anti);
+  if ((threadIdx.x & 31) == 0) {
+    if (ups) atomicAdd(out + 2 * rep, ups);
+    if (anti) atomicAdd(out + 2 * rep + 1, anti);
+  }
+}
+
+__global__ void energy_from_obs_kernel(const unsigned long long* __restrict__ obs, int n, double J, double h,
+                                       long long n_bonds, long long n_sites, double* energy) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const double up = (double)obs[2 * r];
+  const double anti = (double)obs[2 * r + 1];
+  energy[r] = -J * ((double)n_bonds - 2.0 * anti) - h * (2.0 * up - (double)n_sites);
+}
+
+bool geom_ok(int n_replicas, int rows, int cols) {
+  return n_replicas > 0 && rows > 0 && cols > 0 && cols < (1 << 26) && rows < (1 << 30);
+}
+
+Geom make_geom(int n_replicas, int rows, int cols, int wrap_rows, int wrap_cols, int row0) {
+  Geom g;
+  g.rows = rows;
+  g.cols = cols;
+  g.wpr = words_per_row(cols);
+  g.wrap_rows = wrap_rows ? 1 : 0;
+  g.wrap_cols = wrap_cols ? 1 : 0;
+  g.row0 = row0;
+  g.n_replicas = n_replicas;
+  return g;
+}
+
+unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+int launch_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows, int wrap_cols, int colour,
+                      const uint32_t* d_lut, const int32_t* d_lut_index, uint64_t seed, uint32_t sweep,
+                      uint32_t replica0, int row0, const uint32_t* d_halo_top, const uint32_t* d_halo_bot,
+                      cudaStream_t st) {
+  SweepParams P;
+  P.state = d_state;
+  P.lut = d_lut;
+  P.lut_index = d_lut_index;
+  P.halo_top = d_halo_top;
+  P.halo_bot = d_halo_bot;
+  P.g = make_geom(n_replicas, rows, cols, wrap_rows, wrap_cols, row0);
+  P.colour = colour;
+  P.sweep = sweep;
+  P.replica0 = replica0;
+  P.k0 = (uint32_t)seed;
+  P.k1 = (uint32_t)(seed >> 32);
+  const bool rows_closed = (wrap_rows && !d_halo_top && !d_halo_bot) || (d_halo_top && d_halo_bot);
+  const bool fast = wrap_cols && (cols % 256 == 0) && rows_closed;
+  if (fast) {
+    const int nvec = P.g.wpr / 4;
+    // strips long enough to amortise the two halo rows, short enough to fill 148 SMs x 16 warps
+    const long long target_threads = 148LL * 2048;
+    int strip = 64;
+    while (strip > 1 && (long long)n_replicas * nvec * ((rows + strip - 1) / strip) < target_threads) strip >>= 1;
+    P.strip_rows = strip;
+    P.n_strips = (rows + strip - 1) / strip;
+    const long long total = (long long)n_replicas * P.n_strips * nvec;
+    half_sweep_fast_kernel<<<blocks_for(total, 128), 128, 0, st>>>(P);
+  } else {
+    P.strip_rows = 1;
+    P.n_strips = rows;
+    const long long total = (long long)n_replicas * rows * P.g.wpr;
+    half_sweep_generic_kernel<<<blocks_for(total, 128), 128, 0, st>>>(P);
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? TSU_OK : (int)e;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t tsu_ising2d_words_per_row(int cols) { return cols > 0 ? words_per_row(cols) : 0; }
+
+int64_t tsu_ising2d_state_words(int rows, int cols) {
+  return (rows > 0 && cols > 0) ? 2LL * rows * words_per_row(cols) : 0;
+}
+
+int tsu_ising2d_init_random(uint32_t* d_state, int n_replicas, int rows, int cols, uint64_t seed, uint32_t replica0,
+                            int row0, uintptr_t stream) {
+  TSU_CHECK_ARG(d_state && geom_ok(n_replicas, rows, cols) && row0 >= 0);
+  Geom g = make_geom(n_replicas, rows, cols, 0, 0, row0);
+  const long long total = 2LL * rows * g.wpr * n_replicas;
+  init_random_kernel<<<blocks_for(total, 256), 256, 0, tsu_stream(stream)>>>(d_state, g, replica0, (uint32_t)seed,
+                                                                            (uint32_t)(seed >> 32));
+  TSU_RETURN_LAUNCH_STATUS();
+}
+
+int tsu_ising2d_pack(const int8_t* d_spins, uint32_t* d_state, int n_replicas, int rows, int cols, uintptr_t stream) {
+  TSU_CHECK_ARG(d_spins && d_state && geom_ok(n_replicas, rows, cols));
+  Geom g = make_geom(n_replicas, rows, cols, 0, 0, 0);
+  const long long total = 2LL * rows * g.wpr * n_replicas;
+  pack_kernel<<<blocks_for(total, 256), 256, 0, tsu_stream(stream)>>>(d_spins, d_state, g);
+  TSU_RETURN_LAUNCH_STATUS();
+}
+
+int tsu_ising2d_unpack(const uint32_t* d_state, int8_t* d_spins, int n_replicas, int rows, int cols, int as_pm1,
+                       uintptr_t stream) {
+  TSU_CHECK_ARG(d_spins && d_state && geom_ok(n_replicas, rows, cols));
+  Geom g = make_geom(n_replicas, rows, cols, 0, 0, 0);
+  const long long total = 2LL * rows * g.wpr * n_replicas;
+  unpack_kernel<<<blocks_for(total, 256), 256, 0, tsu_stream(stream)>>>(d_state, d_spins, g, as_pm1);
+  TSU_RETURN_LAUNCH_STATUS();
+}
+
+int tsu_ising2d_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows, int wrap_cols,
+                           int colour, const uint32_t* d_lut, const int32_t* d_lut_index, uint64_t seed,
+                           uint32_t sweep, uint32_t replica0, int row0, const uint32_t* d_halo_top,
+                           const uint32_t* d_halo_bot, uintptr_t stream) {
+  TSU_CHECK_ARG(d_state && d_lut && geom_ok(n_replicas, rows, cols) && row0 >= 0);
+  TSU_CHECK_ARG(colour == 0 || colour == 1);
+  TSU_CHECK_ARG(!wrap_cols || (cols % 2 == 0 && cols > 2));
+  TSU_CHECK_ARG(!wrap_rows || (rows % 2 == 0 && rows > 2) || d_halo_top || d_halo_bot);
+  return launch_half_sweep(d_state, n_replicas, rows, cols, wrap_rows, wrap_cols, colour, d_lut, d_lut_index, seed,
+                           sweep, replica0, row0, d_halo_top, d_halo_bot, tsu_stream(stream));
+}
+
+int tsu_ising2d_sweeps(uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows, int wrap_cols,
+                       const uint32_t* d_lut, const int32_t* d_lut_index, uint64_t seed, uint32_t sweep0, int n_sweeps,
+                       uint32_t replica0, uintptr_t stream) {
+  TSU_CHECK_ARG(d_state && d_lut && geom_ok(n_replicas, rows, cols) && n_sweeps >= 0);
+  TSU_CHECK_ARG(!wrap_cols || (cols % 2 == 0 && cols > 2));
+  TSU_CHECK_ARG(!wrap_rows || (rows % 2 == 0 && rows > 2));
+  for (int t = 0; t < n_sweeps; ++t) {
+    for (int colour = 0; colour < 2; ++colour) {
+      int rc = launch_half_sweep(d_state, n_replicas, rows, cols, wrap_rows, wrap_cols, colour, d_lut, d_lut_index,
+                                 seed, sweep0 + (uint32_t)t, replica0, 0, nullptr, nullptr, tsu_stream(stream));
+      if (rc != TSU_OK) return rc;
+    }
+  }
+  return TSU_OK;
+}
+
+int tsu_ising2d_half_sweep_injected(uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows,
+                                    int wrap_cols, int colour, const uint32_t* d_lut, const int32_t* d_lut_index,
+                                    const uint32_t* d_uniforms, int row0, const uint32_t* d_halo_top,
+                                    const uint32_t* d_halo_bot, uintptr_t stream) {
+  TSU_CHECK_ARG(d_state && d_lut && d_uniforms && geom_ok(n_replicas, rows, cols) && row0 >= 0);
+  TSU_CHECK_ARG(colour == 0 || colour == 1);
+  TSU_CHECK_ARG(!wrap_cols || (cols % 2 == 0 && cols > 2));
+  TSU_CHECK_ARG(!wrap_rows || (rows % 2 == 0 && rows > 2) || d_halo_top || d_halo_bot);
+  SweepParams P;
+  P.state = d_state;
+  P.lut = d_lut;
+  P.lut_index = d_lut_index;
+  P.halo_top = d_halo_top;
+  P.halo_bot = d_halo_bot;
+  P.g = make_geom(n_replicas, rows, cols, wrap_rows, wrap_cols, row0);
+  P.colour = colour;
+  P.sweep = 0;
+  P.replica0 = 0;
+  P.k0 = P.k1 = 0;
+  P.strip_rows = 1;
+  P.n_strips = rows;
+  const long long total = (long long)n_replicas * rows * P.g.wpr;
+  half_sweep_injected_kernel<<<blocks_for(total, 128), 128, 0, tsu_stream(stream)>>>(P, d_uniforms);
+  TSU_RETURN_LAUNCH_STATUS();
+}
+
+int tsu_ising2d_observables(const uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows, int wrap_cols,
+                            int row0, const uint32_t* d_next_rows, unsigned long long* d_out, uintptr_t stream) {
+  TSU_CHECK_ARG(d_state && d_out && geom_ok(n_replicas, rows, cols) && row0 >= 0);
+  TSU_CHECK_ARG(n_replicas <= 65535);
+  Geom g = make_geom(n_replicas, rows, cols, wrap_rows, wrap_cols, row0);
+  cudaStream_t st = tsu_stream(stream);
+  cudaError_t e = cudaMemsetAsync(d_out, 0, sizeof(unsigned long long) * 2 * (size_t)n_replicas, st);
+  if (e != cudaSuccess) return (int)e;
+  const long long n_words = 2LL * rows * g.wpr;
+  long long bx = (n_words + 255) / 256;
+  const long long cap = (148LL * 8 + n_replicas - 1) / n_replicas;  // about 8 CTAs per SM in total
+  if (bx > cap) bx = cap < 1 ? 1 : cap;
+  dim3 grid((unsigned)bx, (unsigned)n_replicas);
+  observables_kernel<<<grid, 256, 0, st>>>(d_state, g, d_next_rows, d_out);
+  TSU_RETURN_LAUNCH_STATUS();
+}
+
+int tsu_ising2d_energy_from_observables(const unsigned long long* d_obs, int n_replicas, double J, double h,
+                                        int64_t n_bonds, int64_t n_sites, double* d_energy, uintptr_t stream) {
+  TSU_CHECK_ARG(d_obs && d_energy && n_replicas > 0);
+  energy_from_obs_kernel<<<blocks_for(n_replicas, 128), 128, 0, tsu_stream(stream)>>>(d_obs, n_replicas, J, h, n_bonds,
+                                                                                    n_sites, d_energy);
+  TSU_RETURN_LAUNCH_STATUS();
+}
+
+}  // extern "C"
