@@ -168,12 +168,14 @@ int tsu_pt_swap(const double* d_energy, const double* d_T_slot, int32_t* d_slot_
  * built-in analytic energies: every "sample" of the reference is an independent restarted chain
  * (core.py:140-143), so n_samples chains run in parallel, one per thread, state in registers.
  *   step (core.py:64-80):  x <- x - grad E(x) dt/gamma + sqrt(2 T dt / gamma) N(0, I)
- *   chain c starts at x_init (c == 0 and chain0 == 0) or x_init + jitter * N(0, I) (core.py:142-143)
+ *   chain c starts at x_init + jitter * N(0, I) (core.py:142-143), except local chain 0 when
+ *     first_chain_exact != 0, which starts exactly at x_init like the reference's first sample
  *   energy_kind / d_params (float64 device array):
  *     0 QUADRATIC    E = a * sum_i ((x_i - mu_i)^2 * w_i)         params = [a, mu[dim], w[dim]]
  *     1 MIXTURE      E = -log(sum_k p_k exp(-|x - c_k|^2 / 2) + 1e-10)   (tsu/api.py:143-149)
  *                                                                 params = [K, p[K], c[K][dim]]
  *     2 DOUBLE_WELL  E = sum_i a (x_i^2 - b)^2                    params = [a, b]
+ *     3 QUADRATIC_FORM E = 1/2 x^T A x - b^T x                    params = [A[dim][dim], b[dim]]
  *   dtype 0 = float32, 1 = float64 for d_x / d_x_init / d_traj / d_normals.
  *   d_x: [n_chains][dim] final states (the reference's `samples`).
  *   d_traj: [n_chains][n_steps][dim] sampling-phase trajectory or NULL (core.py:155-156).
@@ -182,7 +184,7 @@ int tsu_pt_swap(const double* d_energy, const double* d_T_slot, int32_t* d_slot_
  */
 int tsu_langevin_run(void* d_x, int dtype, int64_t n_chains, int dim, int energy_kind,
                      const double* d_params, int n_params, const void* d_x_init, double jitter,
-                     double T, double dt, double gamma, int n_burnin, int n_steps, uint64_t seed,
+                     int first_chain_exact, double T, double dt, double gamma, int n_burnin, int n_steps, uint64_t seed,
                      uint64_t chain0, const void* d_normals, void* d_traj, uintptr_t stream);
 
 #ifdef __cplusplus

@@ -77,8 +77,8 @@ SIGNATURES = {
     ),
     "tsu_langevin_run": (
         c_int,
-        [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_double, c_double, c_double, c_double,
-         c_int, c_int, c_uint64, c_uint64, c_void_p, c_void_p, c_uintptr],
+        [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_double, c_int, c_double, c_double,
+         c_double, c_int, c_int, c_uint64, c_uint64, c_void_p, c_void_p, c_uintptr],
     ),
 }
 

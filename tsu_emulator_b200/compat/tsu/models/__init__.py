@@ -1,0 +1,1 @@
+from tsu_emulator_b200.models import *  # noqa: F401,F403

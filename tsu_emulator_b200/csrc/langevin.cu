@@ -18,7 +18,7 @@
 
 namespace {
 
-enum { ENERGY_QUADRATIC = 0, ENERGY_MIXTURE = 1, ENERGY_DOUBLE_WELL = 2 };
+enum { ENERGY_QUADRATIC = 0, ENERGY_MIXTURE = 1, ENERGY_DOUBLE_WELL = 2, ENERGY_QUADRATIC_FORM = 3 };
 
 constexpr int kMaxDynDim = 64;
 
@@ -32,6 +32,7 @@ struct LangevinParams {
   unsigned long long chain0;
   int dim, energy_kind, n_params;
   int n_burnin, n_steps;
+  int first_chain_exact;
   double jitter, drift, noise;  // drift = dt / gamma, noise = sqrt(2 T dt / gamma)
   uint32_t k0, k1;
 };
@@ -121,6 +122,17 @@ __device__ __forceinline__ void gradient(int kind, int dim, const real* __restri
 #pragma unroll
     for (int i = 0; i < MAXD; ++i)
       if (i < dim) g[i] = a4 * x[i] * (x[i] * x[i] - b);
+  } else if (kind == ENERGY_QUADRATIC_FORM) {
+    // E = 1/2 x^T A x - b^T x ; sp = [A[dim][dim], b[dim]] ; grad = A x - b
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i)
+      if (i < dim) {
+        real acc = -sp[dim * dim + i];
+#pragma unroll
+        for (int j = 0; j < MAXD; ++j)
+          if (j < dim) acc += sp[i * dim + j] * x[j];
+        g[i] = acc;
+      }
   } else {
     // E = -log(sum_k p_k exp(-|x - c_k|^2 / 2) + 1e-10); grad = sum_k p_k e_k (x - c_k) / (sum_k p_k e_k + 1e-10)
     const int K = (int)sp[0];
@@ -168,8 +180,8 @@ __global__ void __launch_bounds__(128) langevin_kernel(LangevinParams P) {
 #pragma unroll
   for (int i = 0; i < MAXD; ++i)
     if (i < dim) x[i] = xi ? xi[i] : (real)0;
-  // every chain but global chain 0 starts at x_init + jitter * N(0, I)  (core.py:142-143)
-  if (chain_g != 0ull && P.jitter != 0.0) {
+  // every chain but the first of a call starts at x_init + jitter * N(0, I)  (core.py:142-143)
+  if (!(chain == 0 && P.first_chain_exact) && P.jitter != 0.0) {
     normal_vector<real, DIM>(P, chain_g, chain, 0, dim, z);
 #pragma unroll
     for (int i = 0; i < MAXD; ++i)
@@ -228,13 +240,14 @@ int dispatch_dim(const LangevinParams& P, cudaStream_t st) {
 }  // namespace
 
 extern "C" int tsu_langevin_run(void* d_x, int dtype, int64_t n_chains, int dim, int energy_kind,
-                                const double* d_params, int n_params, const void* d_x_init, double jitter, double T,
-                                double dt, double gamma, int n_burnin, int n_steps, uint64_t seed, uint64_t chain0,
+                                const double* d_params, int n_params, const void* d_x_init, double jitter,
+                                int first_chain_exact, double T, double dt, double gamma, int n_burnin, int n_steps, uint64_t seed, uint64_t chain0,
                                 const void* d_normals, void* d_traj, uintptr_t stream) {
   TSU_CHECK_ARG(d_x && d_params && n_chains > 0 && dim > 0 && dim <= kMaxDynDim);
   TSU_CHECK_ARG(dtype == 0 || dtype == 1);
   TSU_CHECK_ARG(T > 0 && dt > 0 && gamma > 0 && n_burnin >= 0 && n_steps >= 0);
-  TSU_CHECK_ARG(energy_kind >= 0 && energy_kind <= 2);
+  TSU_CHECK_ARG(energy_kind >= 0 && energy_kind <= 3);
+  if (energy_kind == ENERGY_QUADRATIC_FORM) TSU_CHECK_ARG(n_params == dim * dim + dim);
   if (energy_kind == ENERGY_QUADRATIC) TSU_CHECK_ARG(n_params == 1 + 2 * dim);
   if (energy_kind == ENERGY_DOUBLE_WELL) TSU_CHECK_ARG(n_params == 2);
   if (energy_kind == ENERGY_MIXTURE) TSU_CHECK_ARG(n_params >= 2 + dim && n_params <= 20000);
@@ -252,6 +265,7 @@ extern "C" int tsu_langevin_run(void* d_x, int dtype, int64_t n_chains, int dim,
   P.n_burnin = n_burnin;
   P.n_steps = n_steps;
   P.jitter = jitter;
+  P.first_chain_exact = first_chain_exact;
   P.drift = dt / gamma;
   P.noise = sqrt(2.0 * T * dt / gamma);
   P.k0 = (uint32_t)seed;

@@ -1,0 +1,382 @@
+"""
+Drop-in mirror of the reference's tsu/gibbs.py (GibbsConfig, GibbsSampler, HardwareEmulator) whose
+sweeps run on the B200 through libtsu_b200.so.  Same names, arguments, return types and error
+messages as the reference (file:line cited per method); there is no CPU fallback - without a CUDA
+device every sampling call raises.
+
+Differences that are deliberate and documented:
+  * randomness is Philox4x32-10 keyed by a per-sampler seed instead of the global MT19937 stream.
+    The seed is drawn from numpy's global stream at construction unless `seed=` is given, so
+    `np.random.seed(k)` before constructing a sampler still makes a run reproducible.
+  * extra keyword-only arguments (`n_chains`, `precision`, `seed`, `as_tensor`) expose the batch
+    dimension the reference only emulates serially (gibbs.py:475-479).
+"""
+
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import ptr
+
+
+@dataclass
+class GibbsConfig:
+    """tsu/gibbs.py:19-36 (same fields, defaults and validation messages)"""
+
+    temperature: float = 1.0
+    n_burnin: int = 100
+    n_sweeps: int = 10
+    update_order: str = "sequential"  # 'sequential' or 'random'
+
+    def __post_init__(self):
+        if self.temperature <= 0:
+            raise ValueError("Temperature must be positive")
+        if self.n_burnin < 0:
+            raise ValueError("Burn-in steps must be non-negative")
+        if self.n_sweeps <= 0:
+            raise ValueError("Number of sweeps must be positive")
+        if self.update_order not in ["sequential", "random"]:
+            raise ValueError("Update order must be 'sequential' or 'random'")
+
+
+def _as_square(coupling) -> np.ndarray:
+    J = np.asarray(coupling, dtype=np.float64)
+    n_bits = J.shape[0]
+    if J.shape != (n_bits, n_bits):
+        raise ValueError("Coupling matrix must be square")
+    return J
+
+
+class _DenseProblem:
+    """coupling matrix + bias resident on the device (transposed, see tsu_b200.h)"""
+
+    def __init__(self, coupling, bias, precision: str, device):
+        torch = _lib.require_cuda()
+        J = _as_square(coupling)
+        self.N = J.shape[0]
+        if precision not in ("float64", "float32"):
+            raise ValueError("precision must be 'float64' or 'float32'")
+        self.np_dtype = np.float64 if precision == "float64" else np.float32
+        self.code = 1 if precision == "float64" else 0
+        self.device = device
+        self.Jt = torch.from_numpy(np.ascontiguousarray(J.T.astype(self.np_dtype))).to(device)
+        if bias is not None:
+            b = np.asarray(bias, dtype=np.float64)
+            if b.shape != (self.N,):
+                raise ValueError("bias must have one entry per bit")
+            self.bias = torch.from_numpy(np.ascontiguousarray(b.astype(self.np_dtype))).to(device)
+        else:
+            self.bias = None
+
+
+class GibbsSampler:
+    """tsu/gibbs.py:39-393 on the GPU.
+
+    Every chain is one CTA keeping its N local fields in shared memory (csrc/dense_gibbs.cu); the
+    update rule is the reference's: new bit = 1 iff u < sigmoid(h_i / T), h_i = J[i,:].s + b_i
+    including the self term, sigmoid clamped at |x| > 20.
+    """
+
+    def __init__(self, config: Optional[GibbsConfig] = None, *, seed: Optional[int] = None,
+                 precision: str = "float64", device=None):
+        self.config = config or GibbsConfig()
+        self.sample_count = 0
+        self.precision = precision
+        self._seed = int(seed) if seed is not None else int(np.random.randint(0, 2**31 - 1))
+        self._sweep_counter = 0  # Philox offset: advances with every sweep executed
+        self._chain_counter = 0
+        self._device = device
+
+    # ------------------------------------------------------------------ scalar helpers
+    def _sigmoid(self, x: float) -> float:
+        """tsu/gibbs.py:61-77"""
+        if x > 20:
+            return 1.0
+        elif x < -20:
+            return 0.0
+        return 1.0 / (1.0 + np.exp(-x))
+
+    def _compute_local_field(self, i: int, state: np.ndarray, coupling: np.ndarray,
+                             bias: Optional[np.ndarray] = None) -> float:
+        """tsu/gibbs.py:79-100: h_i = J[i,:].s + b_i (includes the self term)"""
+        h = np.dot(coupling[i, :], state)
+        if bias is not None:
+            h += bias[i]
+        return float(h)
+
+    def compute_energy(self, state: np.ndarray, coupling: np.ndarray, bias: Optional[np.ndarray] = None) -> float:
+        """tsu/gibbs.py:215-236: E = -1/2 s^T J s - b^T s (host arithmetic on one configuration)"""
+        state = np.asarray(state)
+        energy = -0.5 * state.dot(coupling).dot(state)
+        if bias is not None:
+            energy -= np.asarray(bias).dot(state)
+        return float(energy)
+
+    # ------------------------------------------------------------------ device plumbing
+    def _dev(self):
+        torch = _lib.require_cuda()
+        return torch.device(self._device) if self._device is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def _orders(self, n_sweeps: int, N: int, device):
+        """visiting order per sweep: None for 'sequential', fresh permutations for 'random' (gibbs.py:153-157)"""
+        if self.config.update_order == "sequential" or n_sweeps == 0:
+            return None
+        torch = _lib.require_cuda()
+        rng = np.random.Generator(np.random.Philox(key=[self._seed, self._sweep_counter]))
+        perms = np.stack([rng.permutation(N) for _ in range(n_sweeps)]).astype(np.int32)
+        return torch.from_numpy(perms).to(device)
+
+    def _run(self, prob: _DenseProblem, state, *, n_burnin: int, n_samples: int, sweeps_per_sample: int,
+             T_chain=None, T_sweep=None, want_samples=False, want_energy=False, track_best=False,
+             order=None, uniforms=None, visits_per_sweep: int = 0):
+        """one launch of tsu_dense_gibbs_run on `state` (uint8 tensor [n_chains, N], updated in place)"""
+        torch = _lib.require_cuda()
+        device = prob.device
+        n_chains, N = state.shape
+        total = n_burnin + n_samples * sweeps_per_sample
+        if order is None and visits_per_sweep == 0:
+            order = self._orders(total, N, device)
+        samples = torch.empty((n_samples, n_chains, N), dtype=torch.uint8, device=device) if want_samples else None
+        energy = torch.empty(n_chains, dtype=torch.float64, device=device) if (want_energy or track_best) else None
+        best_state = torch.empty((n_chains, N), dtype=torch.uint8, device=device) if track_best else None
+        best_energy = torch.empty(n_chains, dtype=torch.float64, device=device) if track_best else None
+        with torch.cuda.device(device):
+            _lib.call(
+                "tsu_dense_gibbs_run", ptr(prob.Jt), prob.code, ptr(prob.bias), ptr(state), n_chains, N,
+                float(self.config.temperature), ptr(T_chain), ptr(T_sweep), int(n_burnin), int(n_samples),
+                int(sweeps_per_sample), ptr(order), ptr(uniforms), ptr(samples), ptr(energy), int(track_best),
+                ptr(best_state), ptr(best_energy), self._seed, self._sweep_counter & 0xFFFFFFFF,
+                self._chain_counter & 0xFFFFFFFF, prob.code, int(visits_per_sweep), _lib.current_stream(),
+            )
+        self._sweep_counter += total
+        return samples, energy, best_state, best_energy
+
+    def _initial_states(self, prob: _DenseProblem, n_chains: int, initial_state=None):
+        torch = _lib.require_cuda()
+        if initial_state is not None:
+            a = np.asarray(initial_state)
+            if a.ndim == 1:
+                a = np.broadcast_to(a, (n_chains, prob.N))
+            return torch.from_numpy(np.ascontiguousarray((a != 0).astype(np.uint8))).to(prob.device)
+        state = torch.empty((n_chains, prob.N), dtype=torch.uint8, device=prob.device)
+        with torch.cuda.device(prob.device):
+            _lib.call("tsu_dense_init_random", ptr(state), n_chains, prob.N, self._seed ^ 0x5DEECE66D,
+                      (self._chain_counter + self._sweep_counter) & 0xFFFFFFFF, _lib.current_stream())
+        return state
+
+    # ------------------------------------------------------------------ reference API
+    def sample_conditional(self, i: int, state: np.ndarray, coupling: np.ndarray,
+                           bias: Optional[np.ndarray] = None) -> int:
+        """tsu/gibbs.py:102-126: resample bit i given the others (one single-site visit on the device)"""
+        torch = _lib.require_cuda()
+        prob = _DenseProblem(coupling, bias, self.precision, self._dev())
+        st = self._initial_states(prob, 1, np.asarray(state))
+        order = torch.tensor([[int(i)]], dtype=torch.int32, device=prob.device)
+        self._run(prob, st, n_burnin=1, n_samples=0, sweeps_per_sample=0, order=order, visits_per_sweep=1)
+        return int(st[0, int(i)].item())
+
+    def _inject(self, prob, uniforms, orders):
+        """parity mode: float64 uniforms [sweeps, N] (single chain) / [sweeps, chains, N] and orders [sweeps, N]"""
+        torch = _lib.require_cuda()
+        u = o = None
+        if uniforms is not None:
+            a = np.asarray(uniforms, dtype=np.float64)
+            if a.ndim == 2:
+                a = a[:, None, :]
+            u = torch.from_numpy(np.ascontiguousarray(a)).to(prob.device)
+        if orders is not None:
+            o = torch.from_numpy(np.ascontiguousarray(np.asarray(orders, dtype=np.int32))).to(prob.device)
+        return u, o
+
+    def gibbs_sweep(self, state: np.ndarray, coupling: np.ndarray, bias: Optional[np.ndarray] = None,
+                    n_sweeps: int = 1, *, _uniforms=None, _orders=None) -> np.ndarray:
+        """tsu/gibbs.py:128-162: n_sweeps sweeps over all bits; the input is not modified (gibbs.py:150)"""
+        prob = _DenseProblem(coupling, bias, self.precision, self._dev())
+        st = self._initial_states(prob, 1, np.asarray(state))
+        u, o = self._inject(prob, _uniforms, _orders)
+        self._run(prob, st, n_burnin=int(n_sweeps), n_samples=0, sweeps_per_sample=0, uniforms=u, order=o)
+        out = st[0].cpu().numpy().astype(np.asarray(state).dtype if np.asarray(state).dtype.kind in "iu" else np.int64)
+        return out
+
+    def sample_boltzmann(self, coupling: np.ndarray, bias: Optional[np.ndarray] = None, n_samples: int = 1000,
+                         burnin: Optional[int] = None, initial_state: Optional[np.ndarray] = None, *,
+                         n_chains: int = 1, as_tensor: bool = False, _uniforms=None, _orders=None):
+        """tsu/gibbs.py:164-213: burn-in, then n_samples x config.n_sweeps sweeps; one launch.
+
+        n_chains == 1 (default): int array (n_samples, n_bits) like the reference.
+        n_chains > 1: (n_chains, n_samples, n_bits) - independent chains run concurrently.
+        """
+        prob = _DenseProblem(coupling, bias, self.precision, self._dev())
+        burnin = burnin if burnin is not None else self.config.n_burnin
+        st = self._initial_states(prob, int(n_chains), initial_state)
+        u, o = self._inject(prob, _uniforms, _orders)
+        samples, _, _, _ = self._run(prob, st, n_burnin=int(burnin), n_samples=int(n_samples),
+                                     sweeps_per_sample=self.config.n_sweeps, want_samples=True, uniforms=u, order=o)
+        self._chain_counter += int(n_chains)
+        self.sample_count += int(n_samples)
+        if as_tensor:
+            return samples if n_chains > 1 else samples[:, 0]
+        out = samples.cpu().numpy().astype(int)  # (n_samples, n_chains, N)
+        if n_chains == 1:
+            return out[:, 0, :]
+        return np.ascontiguousarray(out.transpose(1, 0, 2))
+
+    def sample(self, J: np.ndarray, n_samples: int = 1000, **kwargs) -> np.ndarray:
+        """README.md:69-80: `sampler.sample(J, n_samples=1000)` -> (n_samples, n_bits) binary configurations"""
+        return self.sample_boltzmann(J, n_samples=n_samples, **kwargs)
+
+    def sample_chains(self, coupling, bias=None, n_chains: int = 1024, n_sweeps: Optional[int] = None,
+                      initial_state=None, as_tensor: bool = False, return_energy: bool = False):
+        """batched entry point: n_chains independent chains, n_sweeps sweeps each, final states returned.
+
+        This is the shape of BASELINE config 3 (dense J, N=4096, 2048 chains, 10 sweeps)."""
+        prob = _DenseProblem(coupling, bias, self.precision, self._dev())
+        n_sweeps = self.config.n_sweeps if n_sweeps is None else int(n_sweeps)
+        st = self._initial_states(prob, int(n_chains), initial_state)
+        _, energy, _, _ = self._run(prob, st, n_burnin=n_sweeps, n_samples=0, sweeps_per_sample=0,
+                                    want_energy=return_energy)
+        self._chain_counter += int(n_chains)
+        out = st if as_tensor else st.cpu().numpy().astype(int)
+        if return_energy:
+            return out, (energy if as_tensor else energy.cpu().numpy())
+        return out
+
+    def parallel_tempering(self, coupling: np.ndarray, temperatures: List[float], bias: Optional[np.ndarray] = None,
+                           n_samples: int = 1000, swap_interval: int = 10, *, _inject=None) -> Tuple[np.ndarray, dict]:
+        """tsu/gibbs.py:238-338: replicas at `temperatures`, n_sweeps sweeps per iteration, adjacent-pair
+        Metropolis swaps every swap_interval iterations, samples from temperature slot 0.
+
+        All replicas advance concurrently (one CTA each); configurations stay in place and the
+        slot -> replica map is permuted by tsu_pt_swap, which reproduces the sequential pair order and
+        the draw-only-if-delta<0 rule of gibbs.py:308-323.  One device->host copy at the end.
+        """
+        torch = _lib.require_cuda()
+        prob = _DenseProblem(coupling, bias, self.precision, self._dev())
+        device = prob.device
+        temps = np.asarray(list(temperatures), dtype=np.float64)
+        R = temps.size
+        if R == 0 or np.any(temps <= 0):
+            raise ValueError("Temperature must be positive")
+        n_sweeps = self.config.n_sweeps
+        T_slot = torch.from_numpy(temps).to(device)
+        slot_replica = torch.arange(R, dtype=torch.int32, device=device)
+        T_chain = T_slot.clone()
+        stats = torch.zeros(2, dtype=torch.int64, device=device)
+        inj = _inject
+        states = self._initial_states(prob, R, None if inj is None else np.asarray(inj["inits"]))
+        bu = None
+        if inj is not None:  # parity mode: draws are given per temperature slot; slot i starts on replica i
+            bu = torch.from_numpy(np.ascontiguousarray(np.asarray(inj["burn_uniforms"]).transpose(1, 0, 2))).to(device)
+        self._run(prob, states, n_burnin=self.config.n_burnin, n_samples=0, sweeps_per_sample=0, T_chain=T_chain,
+                  uniforms=bu)
+        samples = torch.empty((n_samples, prob.N), dtype=torch.uint8, device=device)
+        energies = torch.empty((n_samples, R), dtype=torch.float64, device=device)
+        for it in range(n_samples):
+            su = None
+            if inj is not None:
+                sr_host = slot_replica.cpu().numpy()
+                u_slot = np.asarray(inj["sweep_uniforms"][it])            # [slot, sweep, N]
+                u_rep = np.empty_like(u_slot)
+                u_rep[sr_host] = u_slot                                    # replica sr_host[i] sits at slot i
+                su = torch.from_numpy(np.ascontiguousarray(u_rep.transpose(1, 0, 2))).to(device)
+            _, e, _, _ = self._run(prob, states, n_burnin=n_sweeps, n_samples=0, sweeps_per_sample=0,
+                                   T_chain=T_chain, want_energy=True, uniforms=su)
+            energies[it] = e[slot_replica.long()]          # history is kept per temperature slot (gibbs.py:302-303)
+            if (it + 1) % swap_interval == 0:
+                wu = None
+                if inj is not None:
+                    wu = torch.from_numpy(np.ascontiguousarray(np.asarray(inj["swap_uniforms"][it], dtype=np.float64))).to(device)
+                with torch.cuda.device(device):
+                    _lib.call("tsu_pt_swap", ptr(e), ptr(T_slot), ptr(slot_replica), None, 1, R, self._seed,
+                              (it + 1) & 0xFFFFFFFF, ptr(stats), ptr(wu), _lib.current_stream())
+                T_chain[slot_replica.long()] = T_slot
+            samples[it] = states[slot_replica[0].long()]
+        self._chain_counter += R
+        st = stats.cpu().numpy()
+        sr = slot_replica.cpu().numpy()
+        states_np = states.cpu().numpy().astype(int)
+        en = energies.cpu().numpy()
+        info = {
+            "swap_acceptance_rate": (st[1] / st[0]) if st[0] > 0 else 0,
+            "swap_attempts": int(st[0]),
+            "swap_accepts": int(st[1]),
+            "energies": [list(en[:, i]) for i in range(R)],
+            "final_states": [states_np[sr[i]] for i in range(R)],
+        }
+        return samples.cpu().numpy().astype(int), info
+
+    def simulated_annealing(self, coupling: np.ndarray, bias: Optional[np.ndarray] = None, T_initial: float = 10.0,
+                            T_final: float = 0.1, n_steps: int = 1000, cooling_schedule: str = "exponential", *,
+                            n_chains: int = 1, _uniforms=None, _initial_state=None) -> Tuple[np.ndarray, float]:
+        """tsu/gibbs.py:340-393: one sweep per step at the scheduled temperature, lowest energy tracked.
+
+        The whole anneal is one kernel launch (per-sweep temperature array, on-device best tracking).
+        With n_chains > 1 that many independent anneals run concurrently and the best is returned.
+        """
+        torch = _lib.require_cuda()
+        prob = _DenseProblem(coupling, bias, self.precision, self._dev())
+        steps = np.arange(n_steps, dtype=np.float64)
+        if cooling_schedule == "exponential":
+            Ts = T_initial * (T_final / T_initial) ** (steps / n_steps)
+        else:  # linear
+            Ts = T_initial + (T_final - T_initial) * steps / n_steps
+        st = self._initial_states(prob, int(n_chains), _initial_state)
+        if n_steps > 0:
+            T_sweep = torch.from_numpy(Ts).to(prob.device)
+            self.config.temperature = float(Ts[-1])  # the reference leaves the last T in the config (gibbs.py:382)
+            u, _ = self._inject(prob, _uniforms, None)
+            _, _, best_state, best_energy = self._run(prob, st, n_burnin=int(n_steps), n_samples=0,
+                                                      sweeps_per_sample=0, T_sweep=T_sweep, track_best=True,
+                                                      uniforms=u)
+            be = best_energy.cpu().numpy()
+            k = int(np.argmin(be))
+            state = best_state[k].cpu().numpy().astype(int)
+        else:
+            state = st[0].cpu().numpy().astype(int)
+        self._chain_counter += int(n_chains)
+        J = np.asarray(coupling, dtype=np.float64)
+        return state, self.compute_energy(state, J, None if bias is None else np.asarray(bias, dtype=np.float64))
+
+
+class HardwareEmulator:
+    """tsu/gibbs.py:396-487.  The timing model is the reference's arithmetic; sample_parallel finally runs
+    its `parallel_chains` chains in parallel (the reference loops over them, gibbs.py:475-479)."""
+
+    def __init__(self, n_bits: int = 100, clock_speed_ghz: float = 1.0, parallel_chains: int = 1000):
+        self.n_bits = n_bits
+        self.clock_speed_ghz = clock_speed_ghz
+        self.parallel_chains = parallel_chains
+        self.ns_per_cycle = 1.0 / clock_speed_ghz
+
+    def estimate_hardware_time(self, n_samples: int, n_sweeps_per_sample: int) -> dict:
+        """tsu/gibbs.py:421-448"""
+        time_per_sweep_ns = self.n_bits * self.ns_per_cycle
+        time_per_sample_ns = n_sweeps_per_sample * time_per_sweep_ns
+        batches_needed = int(np.ceil(n_samples / self.parallel_chains))
+        total_time_ns = batches_needed * time_per_sample_ns
+        return {
+            "time_per_sweep_ns": time_per_sweep_ns,
+            "time_per_sample_ns": time_per_sample_ns,
+            "batches_needed": batches_needed,
+            "total_time_ns": total_time_ns,
+            "total_time_us": total_time_ns / 1000,
+            "total_time_ms": total_time_ns / 1e6,
+            "total_time_s": total_time_ns / 1e9,
+            "speedup_vs_classical": None,
+        }
+
+    def sample_parallel(self, coupling: np.ndarray, n_samples: int, temperature: float = 1.0) -> Tuple[np.ndarray, dict]:
+        """tsu/gibbs.py:450-487: min(parallel_chains, n_samples) chains x ceil(n_samples/parallel_chains)
+        samples each (burn-in 100), stacked chain after chain and truncated to n_samples."""
+        config = GibbsConfig(temperature=temperature)
+        sampler = GibbsSampler(config)
+        samples_per_chain = int(np.ceil(n_samples / self.parallel_chains))
+        n_chains = min(self.parallel_chains, n_samples)
+        out = sampler.sample_boltzmann(coupling, n_samples=samples_per_chain, burnin=100, n_chains=n_chains)
+        if n_chains == 1:
+            out = out[None]
+        samples = out.reshape(n_chains * samples_per_chain, -1)[:n_samples]
+        timing = self.estimate_hardware_time(n_samples, config.n_sweeps)
+        return samples, timing

@@ -141,6 +141,26 @@ class Ising2DEngine:
             self.lut_index = torch.from_numpy(inv.astype(np.int32)).to(self.device)
         self._lut_temps = uniq
 
+    def chunk_view(self, start: int, count: int):
+        """engine over replicas [start, start+count) sharing this engine's HBM state (no copy)"""
+        cache = self.__dict__.setdefault("_views", {})
+        key = (int(start), int(count))
+        v = cache.get(key)
+        if v is None:
+            if start < 0 or count <= 0 or start + count > self.n_replicas:
+                raise ValueError("chunk out of range")
+            v = object.__new__(Ising2DEngine)
+            v.__dict__.update({k: val for k, val in self.__dict__.items() if k != "_views"})
+            v.n_replicas = int(count)
+            v.replica0 = self.replica0 + int(start)
+            v.state = self.state[start:start + count]
+            v._obs = self._obs[start:start + count]
+            v.temperatures = self.temperatures if self.temperatures.size == 1 else self.temperatures[start:start + count]
+            cache[key] = v
+        v.lut = self.lut
+        v.lut_index = None if self.lut_index is None else self.lut_index[start:start + count]
+        return v
+
     # ------------------------------------------------------------------ state i/o
     def init_random(self):
         """iid Bernoulli(1/2) spins from the Philox init stream (np.random.randint of gibbs.py:201)."""
