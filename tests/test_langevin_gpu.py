@@ -88,7 +88,10 @@ def test_statistics_gaussian_philox():
     s = tsu.sample_gaussian(mu=5.0, sigma=1.0, n_samples=20000)
     assert abs(s.mean() - 5.0) < 0.05
     s = tsu.sample_gaussian(mu=0.0, sigma=2.0, n_samples=20000)
-    assert abs(s.std() - 2.0) < 0.1
+    # 400 steps of dt=0.01 is one relaxation time for sigma=2: var = sigma^2 (1 - exp(-2 t / sigma^2)) -> std 1.86
+    # (the reference's own tolerance is 0.3, tests/test_core.py:58-66)
+    assert abs(s.std() - 2.0) < 0.3
+    assert abs(s.std() - np.sqrt(4.0 * (1 - np.exp(-2 * 4.0 / 4.0)))) < 0.05
     s = tsu.sample_gaussian(mu=0.0, sigma=1.0, n_samples=1000)
     assert stats.kstest(s, "norm")[1] > 0.01
 
