@@ -46,29 +46,30 @@ def colour_count(cols: int, row: int, colour: int) -> int:
     return (cols - p + 1) // 2
 
 
-def pack_spins(bits: np.ndarray) -> np.ndarray:
-    """bits[R, C] in {0,1}  ->  packed[2, R, wpr] uint32 (colour-major, frozen layout)."""
+def pack_spins(bits: np.ndarray, row0: int = 0) -> np.ndarray:
+    """bits[R, C] in {0,1}  ->  packed[2, R, wpr] uint32 (colour-major, frozen layout); row0 = global
+    index of local row 0 (row slabs)."""
     bits = np.asarray(bits)
     R, C = bits.shape
     wpr = words_per_row(C)
     out = np.zeros((2, R, wpr), dtype=np.uint32)
     for colour in range(2):
         for i in range(R):
-            p = (i + colour) & 1
+            p = (row0 + i + colour) & 1
             row = bits[i, p::2].astype(np.uint64)
             k = np.arange(row.size)
             np.bitwise_or.at(out[colour, i], k >> 5, (row << (k & 31).astype(np.uint64)).astype(np.uint32))
     return out
 
 
-def unpack_spins(packed: np.ndarray, rows: int, cols: int) -> np.ndarray:
+def unpack_spins(packed: np.ndarray, rows: int, cols: int, row0: int = 0) -> np.ndarray:
     """inverse of pack_spins -> bits[R, C] int64 in {0,1}."""
     packed = np.asarray(packed, dtype=np.uint32)
     bits = np.zeros((rows, cols), dtype=np.int64)
     for colour in range(2):
         for i in range(rows):
-            p = (i + colour) & 1
-            n = colour_count(cols, i, colour)
+            p = (row0 + i + colour) & 1
+            n = colour_count(cols, row0 + i, colour)
             k = np.arange(n)
             bits[i, p::2] = (packed[colour, i, k >> 5] >> (k & 31).astype(np.uint32)) & 1
     return bits
@@ -221,6 +222,39 @@ def half_sweep(bits, colour, u32, J, h, T, periodic, bias_mode="physical", row0=
     new = (u < p).astype(bits.dtype)
     bits[mask] = new[mask]
     return bits
+
+
+def half_sweep_slab(local, top, bot, colour, u32, J, h, T, wrap_cols, row0, bias_mode="physical"):
+    """row-slab version of half_sweep: `local` are rows row0 .. row0+R-1 of a larger lattice, `top` / `bot` the
+    full rows above / below the slab (None = open edge).  Updates the sites of `colour` of the local rows in place."""
+    R, C = local.shape
+    ext = np.vstack([np.zeros((1, C), dtype=local.dtype) if top is None else np.asarray(top).reshape(1, C), local,
+                     np.zeros((1, C), dtype=local.dtype) if bot is None else np.asarray(bot).reshape(1, C)])
+    up = np.zeros((R, C), dtype=np.int64)
+    deg = np.zeros((R, C), dtype=np.int64)
+    up += ext[0:R]
+    up += ext[2:R + 2]
+    deg += 2
+    if top is None:
+        deg[0] -= 1
+    if bot is None:
+        deg[-1] -= 1
+    up[:, 1:] += local[:, :-1]
+    deg[:, 1:] += 1
+    up[:, :-1] += local[:, 1:]
+    deg[:, :-1] += 1
+    if wrap_cols:
+        up[:, 0] += local[:, -1]
+        up[:, -1] += local[:, 0]
+        deg[:, 0] += 1
+        deg[:, -1] += 1
+    p = acceptance_probability(J, h, T, up, deg, bias_mode)
+    new = ((u32.astype(np.float64) / 4294967296.0) < p).astype(local.dtype)
+    i = np.arange(R)[:, None] + row0
+    j = np.arange(C)[None, :]
+    mask = ((i + j) & 1) == colour
+    local[mask] = new[mask]
+    return local
 
 
 def checkerboard_sweeps(bits0, u32_per_sweep, J, h, T, periodic, bias_mode="physical"):

@@ -281,7 +281,7 @@ __device__ __forceinline__ void tk_select4(uint32_t T, const uint32_t c2[4], con
 // queued word of row i, draws the low 24 bits of its tie lanes (one Philox call each) and ORs the accepted
 // lanes into the stored word with a global RED.  A warp row (128 words) has ~15 such words: one pass of
 // useful work per lane instead of max-over-lanes(#ties) serial passes with one or two active lanes.
-constexpr int kTieCap = 64;
+constexpr int kTieCap = 96;
 struct TieQueue {
   uint32_t count;
   uint32_t pad[3];
@@ -311,13 +311,15 @@ __device__ __forceinline__ uint32_t resolve_word_ties(uint32_t mask, uint32_t c0
 
 __device__ __forceinline__ void drain_tie_queue(const TieQueue& tp, uint32_t lane, uint32_t* own, const Geom& g,
                                                 uint32_t colour_bits, const uint32_t* __restrict__ lut,
-                                                const Coords& q) {
+                                                const Coords& q, int debug_flags) {
+  if (debug_flags & 2) return;
   const uint32_t n_tie = tp.count;
   for (uint32_t t = lane; t < n_tie; t += 32u) {
     const uint32_t w = tp.word[t], row_l = tp.row[t];
     const uint32_t acc = resolve_word_ties(tp.mask[t], tp.c0[t], tp.c1[t], tp.c2[t], w | colour_bits,
                                            (uint32_t)g.row0 + row_l, lut, q);
-    if (acc) atomicOr(own + (size_t)row_l * g.wpr + w, acc);
+    if (acc && !(debug_flags & 4)) atomicOr(own + (size_t)row_l * g.wpr + w, acc);
+    if ((debug_flags & 4) && acc == 0xdeadbeefu) own[0] = acc;
   }
 }
 
@@ -403,7 +405,8 @@ __global__ void __launch_bounds__(128, MINB) half_sweep_fast_kernel(SweepParams 
     const int row_g = g.row0 + i;
     const int p = (row_g + P.colour) & 1;
     // resolve the words with ties queued by the previous row: one queued word per lane
-    if (it > 0) drain_tie_queue(tqs[(it & 1) ^ 1], lane, own, g, colour_bits, lut, q);
+    // (two rows are batched per queue so that ~30 of the 32 lanes have a word to resolve)
+    if (it > 0 && (it & 1) == 0) drain_tie_queue(tqs[((it >> 1) & 1) ^ 1], lane, own, g, colour_bits, lut, q, P.debug_flags);
     // prefetch the row after next (and the side word of the next row) while this row is computed
     uint4 s2 = s;
     uint32_t side_s = 0u;
@@ -488,8 +491,8 @@ __global__ void __launch_bounds__(128, MINB) half_sweep_fast_kernel(SweepParams 
       *reinterpret_cast<uint4*>(own + (size_t)i * g.wpr + w0) = o;
     }
     {
-      TieQueue& tq = tqs[it & 1];
-      uint32_t base = 0u;
+      TieQueue& tq = tqs[(it >> 1) & 1];
+      uint32_t base = (it & 1) ? tq.count : 0u;  // second row of the pair appends
       if (!(P.debug_flags & 1)) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(128, MINB) half_sweep_fast_kernel(SweepParams 
     s = s2;
     side_c = side_s;
   }
-  drain_tie_queue(tqs[(P.strip_rows & 1) ^ 1], lane, own, g, colour_bits, lut, q);  // ties of the last row
+  drain_tie_queue(tqs[((P.strip_rows - 1) >> 1) & 1], lane, own, g, colour_bits, lut, q, P.debug_flags);  // last pair of rows
 }
 
 // Generic path: any size, open or periodic edges, ragged last word.  One thread per word.

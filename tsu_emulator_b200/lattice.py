@@ -141,6 +141,26 @@ class Ising2DEngine:
             self.lut_index = torch.from_numpy(inv.astype(np.int32)).to(self.device)
         self._lut_temps = uniq
 
+    def set_temperature_tables(self, temperatures, lut_index):
+        """one threshold table per entry of `temperatures` (kept in that order) and an explicit
+        replica -> table map (int32 tensor [n_replicas]); used by replica exchange, which permutes the map"""
+        torch = self._torch
+        temps = np.asarray(temperatures, dtype=np.float64)
+        if np.any(temps <= 0):
+            raise ValueError("Temperature must be positive")
+        luts = np.stack([build_lut(self.coupling, self.field, float(t), self.bias_mode) for t in temps])
+        self.lut = torch.from_numpy(luts.view(np.int32)).to(self.device)
+        self._lut_temps = temps
+        self.set_lut_index(lut_index)
+
+    def set_lut_index(self, lut_index):
+        torch = self._torch
+        idx = torch.as_tensor(lut_index, dtype=torch.int32, device=self.device).contiguous()
+        if idx.numel() != self.n_replicas:
+            raise ValueError("one table index per replica")
+        self.lut_index = idx.clone()
+        self.temperatures = self._lut_temps[self.lut_index.cpu().numpy()] if hasattr(self, "_lut_temps") else self.temperatures
+
     def chunk_view(self, start: int, count: int):
         """engine over replicas [start, start+count) sharing this engine's HBM state (no copy)"""
         cache = self.__dict__.setdefault("_views", {})
