@@ -157,10 +157,14 @@ int tsu_dense_init_random(uint8_t* d_state, int n_chains, int N, uint64_t seed, 
  * only when delta < 0).  Configurations stay in place; d_slot_replica[ladder][i] (the replica
  * currently at temperature slot i) is permuted instead, and d_lut_index[replica] (may be NULL)
  * is updated to the slot for the lattice kernels.  d_stats[0] += attempts, d_stats[1] += accepts.
- * d_uniforms: [n_ladders][R-1] float64 (parity mode) or NULL (Philox 'PTSW', step). */
+ * d_uniforms: [n_ladders][R-1] float64 (parity mode) or NULL (Philox 'PTSW', step).
+ * criterion: 0 = the reference's expression above (bit-parity with gibbs.py:317, which favours moving
+ * HIGH-energy configurations to COLD slots); 1 = detailed-balance Metropolis rule
+ * delta = (1/T_i - 1/T_{i+1}) (E_i - E_{i+1}). */
 int tsu_pt_swap(const double* d_energy, const double* d_T_slot, int32_t* d_slot_replica,
                 int32_t* d_lut_index, int n_ladders, int R, uint64_t seed, uint32_t step,
-                unsigned long long* d_stats, const double* d_uniforms, uintptr_t stream);
+                unsigned long long* d_stats, const double* d_uniforms, int criterion,
+                uintptr_t stream);
 
 /* ------------------------------------------------------------------ Langevin ---------- */
 /*

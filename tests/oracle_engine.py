@@ -108,7 +108,7 @@ class OracleEngine:
         return torch.from_numpy(e)
 
 
-def cpu_swap(seed):
+def cpu_swap(seed, criterion=1):
     """host replica-exchange pass with the kernel's semantics and Philox stream (csrc/dense_gibbs.cu: pt_swap_kernel)"""
     from oracle.philox_ref import philox4x32_10
 
@@ -118,7 +118,7 @@ def cpu_swap(seed):
         for ladder in range(K):
             for i in range(R - 1):
                 ra, rb = sr[ladder, i], sr[ladder, i + 1]
-                delta = (1.0 / T[i] - 1.0 / T[i + 1]) * (e[rb] - e[ra])
+                delta = (1.0 / T[i] - 1.0 / T[i + 1]) * ((e[ra] - e[rb]) if criterion else (e[rb] - e[ra]))
                 acc = delta >= 0
                 if not acc:
                     o = philox4x32_10(i, ladder, step & 0xFFFFFFFF, D.STREAM_PT_SWAP, seed & 0xFFFFFFFF, seed >> 32)

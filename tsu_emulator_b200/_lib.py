@@ -73,7 +73,8 @@ SIGNATURES = {
     "tsu_dense_init_random": (c_int, [c_void_p, c_int, c_int, c_uint64, c_uint32, c_uintptr]),
     "tsu_pt_swap": (
         c_int,
-        [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_uint64, c_uint32, c_void_p, c_void_p, c_uintptr],
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_uint64, c_uint32, c_void_p, c_void_p, c_int,
+         c_uintptr],
     ),
     "tsu_langevin_run": (
         c_int,

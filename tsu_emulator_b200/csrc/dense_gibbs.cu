@@ -238,7 +238,7 @@ __global__ void dense_init_kernel(uint8_t* state, int n_chains, int N, uint32_t 
 __global__ void pt_swap_kernel(const double* __restrict__ energy, const double* __restrict__ T_slot,
                                int32_t* slot_replica, int32_t* lut_index, int n_ladders, int R, uint32_t k0,
                                uint32_t k1, uint32_t step, unsigned long long* stats,
-                               const double* __restrict__ uniforms) {
+                               const double* __restrict__ uniforms, int criterion) {
   const int ladder = blockIdx.x * blockDim.x + threadIdx.x;
   if (ladder >= n_ladders) return;
   int32_t* sr = slot_replica + (size_t)ladder * R;
@@ -246,7 +246,9 @@ __global__ void pt_swap_kernel(const double* __restrict__ energy, const double* 
   for (int i = 0; i + 1 < R; ++i) {
     const int ra = sr[i], rb = sr[i + 1];
     const double Ei = energy[ra], Ej = energy[rb];
-    const double delta = (1.0 / T_slot[i] - 1.0 / T_slot[i + 1]) * (Ej - Ei);
+    // criterion 0: the reference's expression (gibbs.py:317); criterion 1: detailed-balance Metropolis rule,
+    // delta = (beta_i - beta_j)(E_i - E_j)
+    const double delta = (1.0 / T_slot[i] - 1.0 / T_slot[i + 1]) * (criterion ? (Ei - Ej) : (Ej - Ei));
     ++attempts;
     bool acc = delta >= 0.0;
     if (!acc) {  // the uniform is consumed only when delta < 0 (short-circuit `or`, gibbs.py:320)
@@ -369,12 +371,13 @@ int tsu_dense_init_random(uint8_t* d_state, int n_chains, int N, uint64_t seed, 
 
 int tsu_pt_swap(const double* d_energy, const double* d_T_slot, int32_t* d_slot_replica, int32_t* d_lut_index,
                 int n_ladders, int R, uint64_t seed, uint32_t step, unsigned long long* d_stats,
-                const double* d_uniforms, uintptr_t stream) {
+                const double* d_uniforms, int criterion, uintptr_t stream) {
   TSU_CHECK_ARG(d_energy && d_T_slot && d_slot_replica && n_ladders > 0 && R > 0);
+  TSU_CHECK_ARG(criterion == 0 || criterion == 1);
   pt_swap_kernel<<<(n_ladders + 63) / 64, 64, 0, tsu_stream(stream)>>>(d_energy, d_T_slot, d_slot_replica,
                                                                       d_lut_index, n_ladders, R, (uint32_t)seed,
                                                                       (uint32_t)(seed >> 32), step, d_stats,
-                                                                      d_uniforms);
+                                                                      d_uniforms, criterion);
   TSU_RETURN_LAUNCH_STATUS();
 }
 

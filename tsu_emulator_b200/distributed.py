@@ -149,11 +149,12 @@ class LatticeTempering:
     replicas; every `swap_interval` iterations one exchange pass per ladder (pairs i = 0..R-2 in order,
     Metropolis rule of tsu/gibbs.py:308-323).  `engine_factory(n_local, replica0, temperatures_local)` builds
     the engine of this rank's replica range; swap_fn(energy, T_slot, slot_replica, lut_index, K, R, step)
-    performs the pass in place (tsu_pt_swap on GPUs).
+    performs the pass in place (tsu_pt_swap on GPUs).  criterion="metropolis" (default) is the detailed-balance
+    rule; "reference" reproduces the expression of gibbs.py:317 (see include/tsu_b200.h).
     """
 
     def __init__(self, temperatures: Sequence[float], n_ladders: int, engine_factory, swap_fn=None, group=None,
-                 n_sweeps: int = 10, swap_interval: int = 10, seed: int = 0):
+                 n_sweeps: int = 10, swap_interval: int = 10, seed: int = 0, criterion: str = "metropolis"):
         import torch
 
         dist = _dist()
@@ -173,6 +174,9 @@ class LatticeTempering:
         self.lut_index = torch.from_numpy(slot0.astype(np.int32)).to(dev)   # replica -> temperature slot
         self.stats = torch.zeros(2, dtype=torch.int64, device=dev)
         self.iteration = 0
+        if criterion not in ("metropolis", "reference"):
+            raise ValueError("criterion must be 'metropolis' or 'reference'")
+        self.criterion = 1 if criterion == "metropolis" else 0
         self.swap_fn = swap_fn or self._swap_cuda
         # the engine's LUT tables must be ordered by slot: one table per temperature of the ladder
         self.engine.set_temperature_tables(self.temps, self.lut_index[self.start:self.stop])
@@ -182,7 +186,7 @@ class LatticeTempering:
         from ._lib import ptr
 
         _lib.call("tsu_pt_swap", ptr(energy), ptr(T_slot), ptr(slot_replica), ptr(lut_index), K, R, self.seed,
-                  step & 0xFFFFFFFF, ptr(self.stats), None, _lib.current_stream())
+                  step & 0xFFFFFFFF, ptr(self.stats), None, self.criterion, _lib.current_stream())
 
     def gather_energies(self):
         import torch

@@ -290,7 +290,7 @@ class GibbsSampler:
                     wu = torch.from_numpy(np.ascontiguousarray(np.asarray(inj["swap_uniforms"][it], dtype=np.float64))).to(device)
                 with torch.cuda.device(device):
                     _lib.call("tsu_pt_swap", ptr(e), ptr(T_slot), ptr(slot_replica), None, 1, R, self._seed,
-                              (it + 1) & 0xFFFFFFFF, ptr(stats), ptr(wu), _lib.current_stream())
+                              (it + 1) & 0xFFFFFFFF, ptr(stats), ptr(wu), 0, _lib.current_stream())
                 T_chain[slot_replica.long()] = T_slot
             samples[it] = states[slot_replica[0].long()]
         self._chain_counter += R
