@@ -152,6 +152,14 @@ int tsu_dense_energy(const void* d_Jt, int j_dtype, const void* d_bias, const ui
 int tsu_dense_init_random(uint8_t* d_state, int n_chains, int N, uint64_t seed, uint32_t chain0,
                           uintptr_t stream);
 
+/* Tensor-core (tcgen05) evaluation of the local fields of EVERY site for a batch of chains:
+ * d_fields[c][i] = sum_k J[i][k] * state[c][k]  (J bf16 [N][N] row-major, fp32 accumulation in TMEM).
+ * This is _compute_local_field (tsu/gibbs.py:79-100) for all (chain, site) pairs at once; it is the GEMM
+ * stage of the blocked tensor-core sweep and is exported so that it can be validated on its own.
+ * N must be a multiple of 64 and <= 4096. */
+int tsu_dense_tc_debug_fields(const void* d_J_bf16, const uint8_t* d_state, int n_chains, int N,
+                              float* d_fields, uintptr_t stream);
+
 /* Replica-exchange pass (tsu/gibbs.py:308-323): for each ladder, pairs i = 0..R-2 in order;
  * delta = (1/T_i - 1/T_{i+1}) (E_{i+1} - E_i); accept if delta >= 0 or u < exp(delta) (u drawn
  * only when delta < 0).  Configurations stay in place; d_slot_replica[ladder][i] (the replica
