@@ -152,6 +152,19 @@ int tsu_dense_energy(const void* d_Jt, int j_dtype, const void* d_bias, const ui
 int tsu_dense_init_random(uint8_t* d_state, int n_chains, int N, uint64_t seed, uint32_t chain0,
                           uintptr_t stream);
 
+/* Batched dense-J Gibbs sweeps on the tensor cores (BASELINE config 3).  Same sequential heat-bath rule as
+ * tsu_dense_gibbs_run (sites 0..N-1 in order, every update sees all earlier ones), evaluated in blocks of 64
+ * sites: the block's fields for 128 chains are a 128 x 64 x N tcgen05 GEMM (bf16 J and 0/1 spins, fp32
+ * accumulation in TMEM), the in-block dependence is resolved exactly by rank-1 corrections.
+ *   d_J_bf16: [N][N] row-major bf16, row i = couplings into site i (J itself, not the transpose);
+ *   d_bias: [N] float32 or NULL; d_state: [n_chains][N] uint8 bits in place; N % 64 == 0, N <= 4096.
+ *   Uniform of (site, chain, sweep): 24 bits of word (site & 3) of Philox(counter = (site >> 2,
+ *   chain0 + chain, sweep0 + sweep, 'DENT')), compared in fp32 with sigmoid(h/T) (clamped at |x| > 20).
+ *   d_fields_or_null: [n_chains][N] float32, receives the GEMM fields of the LAST sweep (diagnostics). */
+int tsu_dense_gibbs_tc_run(const void* d_J_bf16, const float* d_bias, uint8_t* d_state, int n_chains,
+                           int N, double T, const double* d_T_chain, int n_sweeps, uint64_t seed,
+                           uint32_t sweep0, uint32_t chain0, float* d_fields_or_null, uintptr_t stream);
+
 /* Tensor-core (tcgen05) evaluation of the local fields of EVERY site for a batch of chains:
  * d_fields[c][i] = sum_k J[i][k] * state[c][k]  (J bf16 [N][N] row-major, fp32 accumulation in TMEM).
  * This is _compute_local_field (tsu/gibbs.py:79-100) for all (chain, site) pairs at once; it is the GEMM

@@ -17,6 +17,7 @@ import numpy as np
 from .philox_ref import philox4x32_10
 
 STREAM_DENSE = 0x44454E53
+STREAM_DENSE_TC = 0x44454E54
 STREAM_DENSE_INIT = 0x44494E49
 STREAM_PT_SWAP = 0x50545357
 
@@ -127,3 +128,13 @@ def philox_init_state(seed, chain, N):
     o = philox4x32_10(w, chain, 0, STREAM_DENSE_INIT, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     i = np.arange(N)
     return ((o[0][i >> 5] >> (i & 31).astype(np.uint32)) & 1).astype(np.int64)
+
+
+def philox_uniforms_tc(seed, chain, sweep, N):
+    """uniforms of the tensor-core dense path (csrc/dense_tc.cu): 24 bits of word (site & 3) of
+    Philox(counter = (site >> 2, chain, sweep, 'DENT')), value = (word >> 8) / 2^24 (exact in float32)"""
+    sites = np.arange(N, dtype=np.uint64)
+    o = philox4x32_10(sites >> np.uint64(2), chain, sweep & 0xFFFFFFFF, STREAM_DENSE_TC, seed & 0xFFFFFFFF,
+                      (seed >> 32) & 0xFFFFFFFF)
+    w = np.choose((sites & np.uint64(3)).astype(np.int64), [x.astype(np.uint64) for x in o])
+    return (w >> np.uint64(8)).astype(np.float64) / 16777216.0

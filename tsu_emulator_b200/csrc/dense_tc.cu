@@ -24,9 +24,11 @@
 namespace {
 
 constexpr int kChains = 128;  // chains per CTA = UMMA M = TMEM lanes
-constexpr int kBlk = 64;      // sites per block = UMMA N
+constexpr int kBlk = 32;      // sites per block = UMMA N
 constexpr int kKC = 64;       // K-chunk (sites) per pipeline stage
-constexpr int kStages = 3;
+constexpr int kAStages = 4;   // expanded spin tiles (a stage is reused 4 chunks later, when its MMAs are long done)
+constexpr int kBStages = 12;  // J tile ring
+constexpr int kLook = 8;      // J tiles are requested 8 chunks ahead (L2/HBM latency); ring slack = 4 chunks
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -124,18 +126,19 @@ struct TcParams {
 // shared memory carve-up
 struct TcSmem {
   uint32_t sbits[4096 / 32][kChains];               // chain states, word-major: sbits[w][chain]   (N <= 4096)
-  __align__(128) __nv_bfloat16 a[kStages][kKC / 8][kChains / 8][8][8];  // [k16B][row group][row][8 elems]
-  __align__(128) __nv_bfloat16 b[kStages][kKC / 8][kBlk / 8][8][8];
-  __align__(16) float jblk[kBlk][kBlk + 4];           // J[blk, blk] as fp32: jblk[i'][i]
+  __align__(128) __nv_bfloat16 a[kAStages][kKC / 8][kChains / 8][8][8];  // [k16B][row group][row][8 elems]
+  __align__(128) __nv_bfloat16 b[kBStages][kKC / 8][kBlk / 8][8][8];
+  __align__(16) float jblk[kBlk][kBlk + 4];           // J[blk, blk] as fp32, transposed: jblk[i][i'] = J[i0+i'][i0+i]
   __align__(16) uint4 lut[256];                       // byte -> 8 bf16 (0.0 / 1.0)
-  __align__(8) uint64_t mma_done[kStages];            // stage buffers free again
+  __align__(8) uint64_t a_done[kAStages];             // MMAs that read the A stage have completed
+  __align__(8) uint64_t b_done[kBStages];             // MMAs that read the B stage have completed
   __align__(8) uint64_t acc_done;                     // accumulator complete
   uint32_t tmem_base;
 };
 
 __global__ void __launch_bounds__(128, 1) dense_tc_kernel(TcParams P) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int N = P.N;
   const int chain = blockIdx.x * kChains + tid;          // TMEM lane tid <-> chain
@@ -162,12 +165,13 @@ __global__ void __launch_bounds__(128, 1) dense_tc_kernel(TcParams P) {
     sm.sbits[w][tid] = x;
   }
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(&sm.mma_done[s], 1);
+    for (int s = 0; s < kAStages; ++s) mbar_init(&sm.a_done[s], 1);
+    for (int s = 0; s < kBStages; ++s) mbar_init(&sm.b_done[s], 1);
     mbar_init(&sm.acc_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(&sm.tmem_base)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(&sm.tmem_base)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -179,92 +183,198 @@ __global__ void __launch_bounds__(128, 1) dense_tc_kernel(TcParams P) {
   const float T = P.T_chain ? (float)P.T_chain[chain_ok ? chain : 0] : P.T;
   const float invT = 1.0f / T;
 
-  uint32_t stage_phase = 0;   // bit s = parity to wait for on mma_done[s]
-  uint32_t stage_used = 0;    // bit s = stage s has an MMA group in flight
+  uint32_t a_phase = 0, b_phase = 0;   // bit s = parity to wait for on a_done[s] / b_done[s]
   uint32_t acc_phase = 0;
-  int issue = 0;              // running chunk counter (stage = issue % kStages)
+  // producer position (J tile requests run kLook chunks ahead of consumption, across blocks and sweeps);
+  // all indices are kept incrementally - no divisions in the chunk loop
+  int ld_sweep = 0, ld_blk = 0, ld_cc = 0, ld_stage = 0;
+  long long ld_count = 0;
+  auto load_b = [&]() {
+    if (ld_sweep < P.n_sweeps) {
+      int lkc = ld_cc + (ld_blk >> 1) + 1;  // (ld_blk * kBlk) / kKC == ld_blk / 2
+      if (lkc >= n_chunks) lkc -= n_chunks;
+      if (ld_count >= kBStages) {  // the MMAs of the chunk that used this ring slot kBStages chunks ago
+        mbar_wait(&sm.b_done[ld_stage], (b_phase >> ld_stage) & 1u);
+        b_phase ^= 1u << ld_stage;
+      }
+#pragma unroll
+      for (int p = 0; p < kBlk * 8 / 128; ++p) {
+        const int piece = tid + 128 * p;
+        const int n = piece >> 3, k16 = piece & 7;
+        cp_async16(&sm.b[ld_stage][k16][n >> 3][n & 7][0], P.J + (size_t)(ld_blk * kBlk + n) * N + lkc * kKC + 8 * k16);
+      }
+      ++ld_count;
+      if (++ld_stage == kBStages) ld_stage = 0;
+      if (++ld_cc == n_chunks) {
+        ld_cc = 0;
+        if (++ld_blk == n_blocks) {
+          ld_blk = 0;
+          ++ld_sweep;
+        }
+      }
+    }
+    cp_async_commit();  // (an empty group at the tail keeps the group count uniform)
+  };
+  static_assert(kKC == 2 * kBlk, "chunk index of a block is blk / 2");
+
+  for (int i = 0; i < kLook; ++i) load_b();
+  long long g = 0;  // chunks consumed so far
+  int sa = 0, sb = 0;
 
   for (int sweep = 0; sweep < P.n_sweeps; ++sweep) {
     for (int blk = 0; blk < n_blocks; ++blk) {
       const int i0 = blk * kBlk;
-      // J[blk, blk] as fp32 for the in-block rank-1 corrections
-      for (int e = tid; e < kBlk * kBlk; e += 128) {
-        const int r = e / kBlk, c = e - r * kBlk;
-        sm.jblk[r][c] = __bfloat162float(P.J[(size_t)(i0 + r) * N + i0 + c]);
-      }
+      // diagonal block J[blk, blk]: 8 bf16 per thread now (row i0 + tid/4, columns i0 + 8 (tid%4) ..), used after
+      // the GEMM, so the load latency hides behind the chunk loop
+      const uint4 jd = __ldg(reinterpret_cast<const uint4*>(P.J + (size_t)(i0 + (tid >> 2)) * N + i0 + 8 * (tid & 3)));
       // ---- GEMM: H[chain, i] = sum_k S[chain, k] * J[i0 + i, k] -----------------------------------
       // chunk order: the chunk holding this block's own sites goes last (it is the one the previous
       // block's update has just modified); all other chunks only need older state
-      for (int cc = 0; cc < n_chunks; ++cc) {
-        const int kc = (cc + blk + 1) % n_chunks;  // ends with kc == blk
-        const int st = issue % kStages;
-        if ((stage_used >> st) & 1u) {  // wait until the MMAs that read this stage have completed
-          mbar_wait(&sm.mma_done[st], (stage_phase >> st) & 1u);
-          stage_phase ^= 1u << st;
+      for (int cc = 0; cc < n_chunks; ++cc, ++g) {
+        int kc = cc + (blk >> 1) + 1;  // ends with the chunk holding this block
+        if (kc >= n_chunks) kc -= n_chunks;
+        load_b();
+        if (g >= kAStages) {  // the MMAs of chunk g - kAStages read this A stage
+          mbar_wait(&sm.a_done[sa], (a_phase >> sa) & 1u);
+          a_phase ^= 1u << sa;
         }
-        // B tile: rows i0 .. i0+63 of J, columns kc*64 .. +63  (4 x 16 B per thread, coalesced)
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const int piece = tid + 128 * p;
-          const int n = piece >> 3, k16 = piece & 7;
-          cp_async16(&sm.b[st][k16][n >> 3][n & 7][0], P.J + (size_t)(i0 + n) * N + kc * kKC + 8 * k16);
-        }
-        cp_async_commit();
         // A tile: this chain's 64 bits of the chunk -> 64 bf16 (8 x 16 B, one per 8-element K group)
         {
           const uint32_t w0 = sm.sbits[2 * kc][tid], w1 = sm.sbits[2 * kc + 1][tid];
 #pragma unroll
           for (int k16 = 0; k16 < 8; ++k16) {
             const uint32_t byte = ((k16 < 4 ? w0 : w1) >> (8 * (k16 & 3))) & 0xFFu;
-            *reinterpret_cast<uint4*>(&sm.a[st][k16][tid >> 3][tid & 7][0]) = sm.lut[byte];
+            *reinterpret_cast<uint4*>(&sm.a[sa][k16][tid >> 3][tid & 7][0]) = sm.lut[byte];
           }
         }
-        cp_async_wait<0>();
-        fence_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+        cp_async_wait<kLook>();         // J tile of chunk g has landed (this thread's pieces)
+        fence_async_smem();             // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncthreads();
         if (tid == 0) {
           tc_fence_after();
 #pragma unroll
           for (int j = 0; j < kKC / 16; ++j) {
-            const uint64_t ad = umma_desc(smem_u32(&sm.a[st][2 * j][0][0][0]), (kChains / 8) * 128, 128);
-            const uint64_t bd = umma_desc(smem_u32(&sm.b[st][2 * j][0][0][0]), (kBlk / 8) * 128, 128);
+            const uint64_t ad = umma_desc(smem_u32(&sm.a[sa][2 * j][0][0][0]), (kChains / 8) * 128, 128);
+            const uint64_t bd = umma_desc(smem_u32(&sm.b[sb][2 * j][0][0][0]), (kBlk / 8) * 128, 128);
             umma_bf16(tmem_d, ad, bd, idesc, (cc > 0 || j > 0) ? 1u : 0u);
           }
-          umma_commit(&sm.mma_done[st]);
+          umma_commit(&sm.a_done[sa]);
+          umma_commit(&sm.b_done[sb]);
           if (cc == n_chunks - 1) umma_commit(&sm.acc_done);
         }
-        stage_used |= 1u << st;
-        ++issue;
+        if (++sa == kAStages) sa = 0;
+        if (++sb == kBStages) sb = 0;
       }
+      // diagonal block as fp32, transposed: jblk[i][i'] = J[i0 + i', i0 + i] (what a flip of site i adds to the
+      // field of i')
+      {
+        const uint32_t jw[4] = {jd.x, jd.y, jd.z, jd.w};
+        const int r = tid >> 2, c0 = 8 * (tid & 3);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          sm.jblk[c0 + 2 * e][r] = __uint_as_float(jw[e] << 16);              // bf16 -> fp32 is a 16-bit shift
+          sm.jblk[c0 + 2 * e + 1][r] = __uint_as_float(jw[e] & 0xffff0000u);
+        }
+      }
+      __syncthreads();
       // ---- epilogue: fields out of TMEM, sequential update of the block -------------------------
       mbar_wait(&sm.acc_done, acc_phase);
       acc_phase ^= 1u;
       tc_fence_after();
       float h[kBlk];
       tmem_ld32(tmem_lane + 0, h);
-      tmem_ld32(tmem_lane + 32, h + 32);
+      if (kBlk > 32) tmem_ld32(tmem_lane + 32, h + 32);
       tc_fence_before();
       if (P.bias) {
 #pragma unroll
         for (int i = 0; i < kBlk; ++i) h[i] += __ldg(P.bias + i0 + i);
       }
-      if (P.fields_out && chain_ok) {
+      if (P.fields_out && chain_ok && P.gemm_only) {  // fields as accumulated by the tensor core
 #pragma unroll
         for (int i = 0; i < kBlk; ++i) P.fields_out[(size_t)chain * N + i0 + i] = h[i];
       }
-      (void)invT;
+      if (!P.gemm_only) {
+        // sequential heat-bath update of the 64 sites of this block for this thread's chain (gibbs.py:153-160)
+        static_assert(kBlk == 32, "one state word per block");
+        uint32_t w[1] = {sm.sbits[blk][tid]};
+        const uint32_t chain_g = P.chain0 + (uint32_t)chain;
+        tsu_u32x4 o = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int i = 0; i < kBlk; ++i) {
+          if ((i & 3) == 0)  // one Philox block serves 4 consecutive sites of a chain
+            o = tsu_philox4x32_10((uint32_t)((i0 + i) >> 2), chain_g, P.sweep0 + (uint32_t)sweep, TSU_STREAM_DENSE_TC,
+                                  P.k0, P.k1);
+          const uint32_t r32 = (i & 3) == 0 ? o.x : ((i & 3) == 1 ? o.y : ((i & 3) == 2 ? o.z : o.w));
+          const float u = (float)(r32 >> 8) * (1.0f / 16777216.0f);   // 24-bit uniform, exact in fp32
+          if (P.fields_out && chain_ok) P.fields_out[(size_t)chain * N + i0 + i] = h[i];  // field at visit time
+          const float x = h[i] * invT;
+          float pacc = 1.0f / (1.0f + __expf(-x));                     // gibbs.py:61-77 incl. the clamp
+          pacc = x > 20.0f ? 1.0f : (x < -20.0f ? 0.0f : pacc);
+          const uint32_t nb = u < pacc ? 1u : 0u;                      // gibbs.py:126 (strict <)
+          const uint32_t ob = (w[i >> 5] >> (i & 31)) & 1u;
+          const float delta = (float)nb - (float)ob;
+          w[i >> 5] = (w[i >> 5] & ~(1u << (i & 31))) | (nb << (i & 31));
+          // not yet visited sites of the block see the new value (rank-1 correction, branch free)
+#pragma unroll
+          for (int ip = i + 1; ip < kBlk; ++ip) h[ip] = fmaf(sm.jblk[i][ip], delta, h[ip]);
+        }
+        sm.sbits[blk][tid] = w[0];
+      }
       __syncthreads();  // jblk reuse, sbits of this block final before the next block's last chunk
+    }
+  }
+  if (!P.gemm_only && chain_ok) {  // unpack the final bits of this chain
+    for (int w = 0; w < N / 32; ++w) {
+      const uint32_t x = sm.sbits[w][tid];
+      uint8_t* dst = P.state + (size_t)chain * N + 32 * w;
+#pragma unroll
+      for (int b = 0; b < 32; b += 4) {
+        const uint32_t n4 = (x >> b) & 15u;
+        *reinterpret_cast<uint32_t*>(dst + b) = (n4 & 1u) | ((n4 & 2u) << 7) | ((n4 & 4u) << 14) | ((n4 & 8u) << 21);
+      }
     }
   }
   // ---- teardown ----------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem_d) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem_d) : "memory");
   }
 }
 
 }  // namespace
+
+static int launch_tc(const TcParams& P, cudaStream_t st) {
+  const size_t smem = sizeof(TcSmem);
+  cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  dense_tc_kernel<<<(P.n_chains + kChains - 1) / kChains, 128, smem, st>>>(P);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? TSU_OK : (int)e;
+}
+
+extern "C" int tsu_dense_gibbs_tc_run(const void* d_J_bf16, const float* d_bias, uint8_t* d_state, int n_chains, int N,
+                                      double T, const double* d_T_chain, int n_sweeps, uint64_t seed, uint32_t sweep0,
+                                      uint32_t chain0, float* d_fields_or_null, uintptr_t stream) {
+  TSU_CHECK_ARG(d_J_bf16 && d_state && n_chains > 0 && N > 0 && N % 64 == 0 && N <= 4096 && n_sweeps >= 0);
+  TSU_CHECK_ARG(d_T_chain || T > 0);
+  TcParams P = {};
+  P.J = reinterpret_cast<const __nv_bfloat16*>(d_J_bf16);
+  P.bias = d_bias;
+  P.state = d_state;
+  P.fields_out = d_fields_or_null;
+  P.T_chain = d_T_chain;
+  P.n_chains = n_chains;
+  P.N = N;
+  P.n_sweeps = n_sweeps;
+  P.T = (float)T;
+  P.k0 = (uint32_t)seed;
+  P.k1 = (uint32_t)(seed >> 32);
+  P.sweep0 = sweep0;
+  P.chain0 = chain0;
+  P.gemm_only = 0;
+  return launch_tc(P, tsu_stream(stream));
+}
 
 extern "C" int tsu_dense_tc_debug_fields(const void* d_J_bf16, const uint8_t* d_state, int n_chains, int N,
                                          float* d_fields, uintptr_t stream) {
@@ -278,9 +388,5 @@ extern "C" int tsu_dense_tc_debug_fields(const void* d_J_bf16, const uint8_t* d_
   P.n_sweeps = 1;
   P.T = 1.0f;
   P.gemm_only = 1;
-  const size_t smem = sizeof(TcSmem) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  dense_tc_kernel<<<(n_chains + kChains - 1) / kChains, 128, smem, tsu_stream(stream)>>>(P);
-  TSU_RETURN_LAUNCH_STATUS();
+  return launch_tc(P, tsu_stream(stream));
 }

@@ -68,6 +68,7 @@ __host__ __device__ __forceinline__ tsu_u32x4 tsu_philox4x32_10(uint32_t c0, uin
 // Generic streams (dense Gibbs / Langevin / fill): counter = (index_lo, index_hi, step, stream_tag)
 #define TSU_STREAM_FILL 0x46494C4Cu      // 'FILL'
 #define TSU_STREAM_DENSE 0x44454E53u     // 'DENS'
+#define TSU_STREAM_DENSE_TC 0x44454E54u  // 'DENT': tensor-core dense path, counter = (site>>2, chain, sweep, tag)
 #define TSU_STREAM_DENSE_INIT 0x44494E49u  // 'DINI'
 #define TSU_STREAM_LANGEVIN 0x4C414E47u  // 'LANG'
 #define TSU_STREAM_LANGEVIN_INIT 0x4C494E49u  // 'LINI'

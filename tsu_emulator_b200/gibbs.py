@@ -227,11 +227,55 @@ class GibbsSampler:
         """README.md:69-80: `sampler.sample(J, n_samples=1000)` -> (n_samples, n_bits) binary configurations"""
         return self.sample_boltzmann(J, n_samples=n_samples, **kwargs)
 
+    def _sample_chains_tensor(self, coupling, bias, n_chains, n_sweeps, initial_state, as_tensor, return_energy):
+        """tensor-core path (csrc/dense_tc.cu): bf16 couplings, fp32 fields accumulated in TMEM"""
+        torch = _lib.require_cuda()
+        device = self._dev()
+        J = _as_square(coupling)
+        N = J.shape[0]
+        if N % 64 or N > 4096:
+            raise ValueError("the tensor-core path needs N % 64 == 0 and N <= 4096")
+        if self.config.update_order != "sequential":
+            raise ValueError("the tensor-core path implements the sequential update order")
+        Jd = torch.from_numpy(np.ascontiguousarray(J)).to(device=device, dtype=torch.bfloat16).contiguous()
+        bd = None
+        if bias is not None:
+            bd = torch.from_numpy(np.ascontiguousarray(np.asarray(bias, dtype=np.float32))).to(device)
+
+        class _P:  # minimal problem record for _initial_states
+            pass
+        prob = _P()
+        prob.N, prob.device = N, device
+        st = self._initial_states(prob, int(n_chains), initial_state)
+        with torch.cuda.device(device):
+            _lib.call("tsu_dense_gibbs_tc_run", ptr(Jd), ptr(bd), ptr(st), int(n_chains), N,
+                      float(self.config.temperature), None, int(n_sweeps), self._seed,
+                      self._sweep_counter & 0xFFFFFFFF, self._chain_counter & 0xFFFFFFFF, None, _lib.current_stream())
+        self._sweep_counter += int(n_sweeps)
+        self._chain_counter += int(n_chains)
+        energy = None
+        if return_energy:  # E = -1/2 s^T J s - b^T s from one more tensor-core field evaluation
+            H = torch.empty((n_chains, N), dtype=torch.float32, device=device)
+            with torch.cuda.device(device):
+                _lib.call("tsu_dense_tc_debug_fields", ptr(Jd), ptr(st), int(n_chains), N, ptr(H), _lib.current_stream())
+            sf = st.to(torch.float64)
+            energy = -0.5 * (sf * H.to(torch.float64)).sum(1)
+            if bd is not None:
+                energy = energy - sf @ bd.to(torch.float64)
+        out = st if as_tensor else st.cpu().numpy().astype(int)
+        if return_energy:
+            return out, (energy if as_tensor else energy.cpu().numpy())
+        return out
+
     def sample_chains(self, coupling, bias=None, n_chains: int = 1024, n_sweeps: Optional[int] = None,
                       initial_state=None, as_tensor: bool = False, return_energy: bool = False):
         """batched entry point: n_chains independent chains, n_sweeps sweeps each, final states returned.
 
-        This is the shape of BASELINE config 3 (dense J, N=4096, 2048 chains, 10 sweeps)."""
+        This is the shape of BASELINE config 3 (dense J, N=4096, 2048 chains, 10 sweeps).  With
+        precision="bf16" the fields are evaluated on the tensor cores (tcgen05, csrc/dense_tc.cu)."""
+        if self.precision == "bf16":
+            n_sw = self.config.n_sweeps if n_sweeps is None else int(n_sweeps)
+            return self._sample_chains_tensor(coupling, bias, n_chains, n_sw, initial_state, as_tensor, return_energy)
         prob = _DenseProblem(coupling, bias, self.precision, self._dev())
         n_sweeps = self.config.n_sweeps if n_sweeps is None else int(n_sweeps)
         st = self._initial_states(prob, int(n_chains), initial_state)
