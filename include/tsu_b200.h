@@ -157,7 +157,7 @@ int tsu_dense_init_random(uint8_t* d_state, int n_chains, int N, uint64_t seed, 
  * sites: the block's fields for 128 chains are a 128 x 64 x N tcgen05 GEMM (bf16 J and 0/1 spins, fp32
  * accumulation in TMEM), the in-block dependence is resolved exactly by rank-1 corrections.
  *   d_J_bf16: [N][N] row-major bf16, row i = couplings into site i (J itself, not the transpose);
- *   d_bias: [N] float32 or NULL; d_state: [n_chains][N] uint8 bits in place; N % 64 == 0, N <= 4096.
+ *   d_bias: [N] float32 or NULL; d_state: [n_chains][N] uint8 bits in place; N % 128 == 0, N <= 4096.
  *   Uniform of (site, chain, sweep): 24 bits of word (site & 3) of Philox(counter = (site >> 2,
  *   chain0 + chain, sweep0 + sweep, 'DENT')), compared in fp32 with sigmoid(h/T) (clamped at |x| > 20).
  *   d_fields_or_null: [n_chains][N] float32, receives the GEMM fields of the LAST sweep (diagnostics). */
@@ -169,7 +169,7 @@ int tsu_dense_gibbs_tc_run(const void* d_J_bf16, const float* d_bias, uint8_t* d
  * d_fields[c][i] = sum_k J[i][k] * state[c][k]  (J bf16 [N][N] row-major, fp32 accumulation in TMEM).
  * This is _compute_local_field (tsu/gibbs.py:79-100) for all (chain, site) pairs at once; it is the GEMM
  * stage of the blocked tensor-core sweep and is exported so that it can be validated on its own.
- * N must be a multiple of 64 and <= 4096. */
+ * N must be a multiple of 128 and <= 4096. */
 int tsu_dense_tc_debug_fields(const void* d_J_bf16, const uint8_t* d_state, int n_chains, int N,
                               float* d_fields, uintptr_t stream);
 

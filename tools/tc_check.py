@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from tsu_emulator_b200 import _lib
-N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 256  # multiple of 128
 C = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 torch.manual_seed(0)
 J = (torch.randn(N, N, device="cuda") / N**0.5).to(torch.bfloat16)

@@ -25,10 +25,10 @@ namespace {
 
 constexpr int kChains = 128;  // chains per CTA = UMMA M = TMEM lanes
 constexpr int kBlk = 32;      // sites per block = UMMA N
-constexpr int kKC = 64;       // K-chunk (sites) per pipeline stage
-constexpr int kAStages = 4;   // expanded spin tiles (a stage is reused 4 chunks later, when its MMAs are long done)
-constexpr int kBStages = 12;  // J tile ring
-constexpr int kLook = 8;      // J tiles are requested 8 chunks ahead (L2/HBM latency); ring slack = 4 chunks
+constexpr int kKC = 128;      // K-chunk (sites) per pipeline stage
+constexpr int kAStages = 3;   // expanded spin tiles (32 KB each)
+constexpr int kBStages = 6;   // J tile ring (8 KB each)
+constexpr int kLook = 4;      // J tiles are requested 4 chunks (512 sites) ahead of their use
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -114,190 +114,238 @@ struct TcParams {
   const __nv_bfloat16* J;   // [N][N] row-major coupling matrix (row i = couplings INTO site i)
   const float* bias;        // [N] or nullptr
   uint8_t* state;           // [n_chains][N] bits, updated in place
-  float* fields_out;        // debug: [n_chains][N] fields seen at visit time (nullptr in production)
+  float* fields_out;        // diagnostics: [n_chains][N] field of every site at the time it was visited
   const double* T_chain;    // [n_chains] or nullptr
-  double* energy;           // [n_chains] or nullptr
   int n_chains, N, n_sweeps;
   float T;
   uint32_t k0, k1, sweep0, chain0;
-  int gemm_only;            // debug: skip the spin update (fields of the initial state for every site)
+  int gemm_only;            // diagnostics: no spin update (fields of the initial state for every site)
 };
 
-// shared memory carve-up
+constexpr int kThreads = 288;  // warps 0-3 producers, 4-7 epilogue (chain = lane of TMEM), 8 MMA issuer
+
+// shared memory carve-up (217 KB)
 struct TcSmem {
-  uint32_t sbits[4096 / 32][kChains];               // chain states, word-major: sbits[w][chain]   (N <= 4096)
-  __align__(128) __nv_bfloat16 a[kAStages][kKC / 8][kChains / 8][8][8];  // [k16B][row group][row][8 elems]
+  uint32_t sbits[4096 / 32][kChains];                                     // chain states, word-major: sbits[w][chain]
+  __align__(128) __nv_bfloat16 a[kAStages][kKC / 8][kChains / 8][8][8];   // [k16B][row group][row][8 elems]
   __align__(128) __nv_bfloat16 b[kBStages][kKC / 8][kBlk / 8][8][8];
-  __align__(16) float jblk[kBlk][kBlk + 4];           // J[blk, blk] as fp32, transposed: jblk[i][i'] = J[i0+i'][i0+i]
-  __align__(16) uint4 lut[256];                       // byte -> 8 bf16 (0.0 / 1.0)
-  __align__(8) uint64_t a_done[kAStages];             // MMAs that read the A stage have completed
-  __align__(8) uint64_t b_done[kBStages];             // MMAs that read the B stage have completed
-  __align__(8) uint64_t acc_done;                     // accumulator complete
+  __align__(16) float jblk[kBlk][kBlk + 4];  // J[blk, blk] as fp32, transposed: jblk[i][i'] = J[i0+i'][i0+i]
+  __align__(16) uint4 lut[256];              // byte -> 8 bf16 (0.0 / 1.0)
+  __align__(8) uint64_t full[kAStages];      // producers -> MMA: A stage written, J tile landed      (count 128)
+  __align__(8) uint64_t a_empty[kAStages];   // MMA -> producers: the MMAs that read the A stage are done (commit)
+  __align__(8) uint64_t b_empty[kBStages];   // MMA -> producers: J ring slot free                       (commit)
+  __align__(8) uint64_t acc_full[2];         // MMA -> epilogue: accumulator buffer complete             (commit)
+  __align__(8) uint64_t acc_free[2];         // epilogue -> MMA: accumulator buffer read out             (count 128)
+  __align__(8) uint64_t state_ready;         // epilogue -> producers: bits of the block written         (count 128)
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(128, 1) dense_tc_kernel(TcParams P) {
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int N = P.N;
-  const int chain = blockIdx.x * kChains + tid;          // TMEM lane tid <-> chain
-  const bool chain_ok = chain < P.n_chains;
   const int n_blocks = N / kBlk, n_chunks = N / kKC;
+  const int total_blocks = n_blocks * P.n_sweeps;
+  static_assert(kKC == 4 * kBlk, "a K-chunk holds four blocks");
 
   // ---- one-time setup -------------------------------------------------------------------------
-  for (int i = tid; i < 256; i += 128) {
+  for (int i = tid; i < 256; i += kThreads) {
     uint32_t w[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) w[p] = ((i >> (2 * p)) & 1 ? 0x3F80u : 0u) | ((i >> (2 * p + 1)) & 1 ? 0x3F800000u : 0u);
     sm.lut[i] = make_uint4(w[0], w[1], w[2], w[3]);
   }
-  for (int w = 0; w < N / 32; ++w) {  // pack this chain's bits
-    uint32_t x = 0;
-    if (chain_ok) {
-      const uint8_t* src = P.state + (size_t)chain * N + 32 * w;
+  if (tid < kChains) {  // pack this chain's bits
+    const int chain = blockIdx.x * kChains + tid;
+    for (int w = 0; w < N / 32; ++w) {
+      uint32_t x = 0;
+      if (chain < P.n_chains) {
+        const uint8_t* src = P.state + (size_t)chain * N + 32 * w;
 #pragma unroll
-      for (int b = 0; b < 32; b += 4) {
-        const uint32_t v = *reinterpret_cast<const uint32_t*>(src + b);
-        x |= ((v & 1u) | ((v >> 7) & 2u) | ((v >> 14) & 4u) | ((v >> 21) & 8u)) << b;
+        for (int b = 0; b < 32; b += 4) {
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(src + b);
+          x |= ((v & 1u) | ((v >> 7) & 2u) | ((v >> 14) & 4u) | ((v >> 21) & 8u)) << b;
+        }
       }
+      sm.sbits[w][tid] = x;
     }
-    sm.sbits[w][tid] = x;
   }
   if (tid == 0) {
-    for (int s = 0; s < kAStages; ++s) mbar_init(&sm.a_done[s], 1);
-    for (int s = 0; s < kBStages; ++s) mbar_init(&sm.b_done[s], 1);
-    mbar_init(&sm.acc_done, 1);
+    for (int s = 0; s < kAStages; ++s) {
+      mbar_init(&sm.full[s], kChains);
+      mbar_init(&sm.a_empty[s], 1);
+    }
+    for (int s = 0; s < kBStages; ++s) mbar_init(&sm.b_empty[s], 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sm.acc_full[s], 1);
+      mbar_init(&sm.acc_free[s], kChains);
+    }
+    mbar_init(&sm.state_ready, kChains);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(&sm.tmem_base)) : "memory");
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(&sm.tmem_base)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = sm.tmem_base;
-  const uint32_t tmem_lane = tmem_d + ((uint32_t)(warp * 32) << 16);
-  const uint32_t idesc = umma_idesc(kChains, kBlk);
-  const float T = P.T_chain ? (float)P.T_chain[chain_ok ? chain : 0] : P.T;
-  const float invT = 1.0f / T;
 
-  uint32_t a_phase = 0, b_phase = 0;   // bit s = parity to wait for on a_done[s] / b_done[s]
-  uint32_t acc_phase = 0;
-  // producer position (J tile requests run kLook chunks ahead of consumption, across blocks and sweeps);
-  // all indices are kept incrementally - no divisions in the chunk loop
-  int ld_sweep = 0, ld_blk = 0, ld_cc = 0, ld_stage = 0;
-  long long ld_count = 0;
-  auto load_b = [&]() {
-    if (ld_sweep < P.n_sweeps) {
-      int lkc = ld_cc + (ld_blk >> 1) + 1;  // (ld_blk * kBlk) / kKC == ld_blk / 2
-      if (lkc >= n_chunks) lkc -= n_chunks;
-      if (ld_count >= kBStages) {  // the MMAs of the chunk that used this ring slot kBStages chunks ago
-        mbar_wait(&sm.b_done[ld_stage], (b_phase >> ld_stage) & 1u);
-        b_phase ^= 1u << ld_stage;
-      }
-#pragma unroll
-      for (int p = 0; p < kBlk * 8 / 128; ++p) {
-        const int piece = tid + 128 * p;
-        const int n = piece >> 3, k16 = piece & 7;
-        cp_async16(&sm.b[ld_stage][k16][n >> 3][n & 7][0], P.J + (size_t)(ld_blk * kBlk + n) * N + lkc * kKC + 8 * k16);
-      }
-      ++ld_count;
-      if (++ld_stage == kBStages) ld_stage = 0;
-      if (++ld_cc == n_chunks) {
-        ld_cc = 0;
-        if (++ld_blk == n_blocks) {
-          ld_blk = 0;
-          ++ld_sweep;
+  if (warp < 4) {
+    // ===================== producers: expand spins to bf16 A tiles, stream J tiles ======================
+    uint32_t a_phase = 0, b_phase = 0, ready_phase = 0;
+    int ld_sweep = 0, ld_blk = 0, ld_cc = 0, ld_stage = 0;
+    long long ld_count = 0;
+    auto load_b = [&]() {  // J tile request, kLook chunks ahead of consumption (across blocks and sweeps)
+      if (ld_sweep < P.n_sweeps) {
+        int lkc = ld_cc + (ld_blk >> 2) + 1;
+        if (lkc >= n_chunks) lkc -= n_chunks;
+        if (ld_count >= kBStages) {
+          mbar_wait(&sm.b_empty[ld_stage], (b_phase >> ld_stage) & 1u);
+          b_phase ^= 1u << ld_stage;
         }
-      }
-    }
-    cp_async_commit();  // (an empty group at the tail keeps the group count uniform)
-  };
-  static_assert(kKC == 2 * kBlk, "chunk index of a block is blk / 2");
-
-  for (int i = 0; i < kLook; ++i) load_b();
-  long long g = 0;  // chunks consumed so far
-  int sa = 0, sb = 0;
-
-  for (int sweep = 0; sweep < P.n_sweeps; ++sweep) {
-    for (int blk = 0; blk < n_blocks; ++blk) {
-      const int i0 = blk * kBlk;
-      // diagonal block J[blk, blk]: 8 bf16 per thread now (row i0 + tid/4, columns i0 + 8 (tid%4) ..), used after
-      // the GEMM, so the load latency hides behind the chunk loop
-      const uint4 jd = __ldg(reinterpret_cast<const uint4*>(P.J + (size_t)(i0 + (tid >> 2)) * N + i0 + 8 * (tid & 3)));
-      // ---- GEMM: H[chain, i] = sum_k S[chain, k] * J[i0 + i, k] -----------------------------------
-      // chunk order: the chunk holding this block's own sites goes last (it is the one the previous
-      // block's update has just modified); all other chunks only need older state
-      for (int cc = 0; cc < n_chunks; ++cc, ++g) {
-        int kc = cc + (blk >> 1) + 1;  // ends with the chunk holding this block
-        if (kc >= n_chunks) kc -= n_chunks;
-        load_b();
-        if (g >= kAStages) {  // the MMAs of chunk g - kAStages read this A stage
-          mbar_wait(&sm.a_done[sa], (a_phase >> sa) & 1u);
-          a_phase ^= 1u << sa;
-        }
-        // A tile: this chain's 64 bits of the chunk -> 64 bf16 (8 x 16 B, one per 8-element K group)
-        {
-          const uint32_t w0 = sm.sbits[2 * kc][tid], w1 = sm.sbits[2 * kc + 1][tid];
 #pragma unroll
-          for (int k16 = 0; k16 < 8; ++k16) {
-            const uint32_t byte = ((k16 < 4 ? w0 : w1) >> (8 * (k16 & 3))) & 0xFFu;
-            *reinterpret_cast<uint4*>(&sm.a[sa][k16][tid >> 3][tid & 7][0]) = sm.lut[byte];
+        for (int p = 0; p < kBlk * (kKC / 8) / kChains; ++p) {
+          const int piece = tid + kChains * p;
+          const int n = piece / (kKC / 8), k16 = piece % (kKC / 8);
+          cp_async16(&sm.b[ld_stage][k16][n >> 3][n & 7][0], P.J + (size_t)(ld_blk * kBlk + n) * N + lkc * kKC + 8 * k16);
+        }
+        ++ld_count;
+        if (++ld_stage == kBStages) ld_stage = 0;
+        if (++ld_cc == n_chunks) {
+          ld_cc = 0;
+          if (++ld_blk == n_blocks) {
+            ld_blk = 0;
+            ++ld_sweep;
           }
         }
-        cp_async_wait<kLook>();         // J tile of chunk g has landed (this thread's pieces)
-        fence_async_smem();             // generic-proxy writes -> visible to the tensor core (async proxy)
-        __syncthreads();
-        if (tid == 0) {
+      }
+      cp_async_commit();  // (an empty group at the tail keeps the group count uniform)
+    };
+    for (int i = 0; i < kLook; ++i) load_b();
+    long long g = 0;
+    int sa = 0;
+    for (int gb = 0; gb < total_blocks; ++gb) {
+      const int blk = gb % n_blocks;
+      for (int cc = 0; cc < n_chunks; ++cc, ++g) {
+        // chunk order: own + 1, ..., own - 1, own.  The two last chunks may hold the previous block's sites,
+        // so they wait for that block's update; everything earlier only needs older state.
+        int kc = cc + (blk >> 2) + 1;
+        if (kc >= n_chunks) kc -= n_chunks;
+        load_b();
+        if (gb > 0 && cc == (n_chunks >= 2 ? n_chunks - 2 : 0)) {
+          mbar_wait(&sm.state_ready, ready_phase);
+          ready_phase ^= 1u;
+        }
+        if (g >= kAStages) {
+          mbar_wait(&sm.a_empty[sa], (a_phase >> sa) & 1u);
+          a_phase ^= 1u << sa;
+        }
+#pragma unroll
+        for (int q = 0; q < kKC / 32; ++q) {
+          const uint32_t w = sm.sbits[(kKC / 32) * kc + q][tid];
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            *reinterpret_cast<uint4*>(&sm.a[sa][4 * q + k4][tid >> 3][tid & 7][0]) = sm.lut[(w >> (8 * k4)) & 0xFFu];
+        }
+        cp_async_wait<kLook>();  // this thread's pieces of the J tile of chunk g have landed
+        fence_async_smem();      // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(&sm.full[sa]);
+        if (++sa == kAStages) sa = 0;
+      }
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer: one thread feeds the tensor core ===============================
+    if ((tid & 31) == 0) {
+      const uint32_t idesc = umma_idesc(kChains, kBlk);
+      uint32_t full_phase = 0, free_phase = 0;
+      int sa = 0, sb = 0;
+      for (int gb = 0; gb < total_blocks; ++gb) {
+        const int buf = gb & 1;
+        if (gb >= 2) {  // the epilogue has read this accumulator buffer out
+          mbar_wait(&sm.acc_free[buf], (free_phase >> buf) & 1u);
+          free_phase ^= 1u << buf;
+        }
+        for (int cc = 0; cc < n_chunks; ++cc) {
+          mbar_wait(&sm.full[sa], (full_phase >> sa) & 1u);
+          full_phase ^= 1u << sa;
           tc_fence_after();
 #pragma unroll
           for (int j = 0; j < kKC / 16; ++j) {
             const uint64_t ad = umma_desc(smem_u32(&sm.a[sa][2 * j][0][0][0]), (kChains / 8) * 128, 128);
             const uint64_t bd = umma_desc(smem_u32(&sm.b[sb][2 * j][0][0][0]), (kBlk / 8) * 128, 128);
-            umma_bf16(tmem_d, ad, bd, idesc, (cc > 0 || j > 0) ? 1u : 0u);
+            umma_bf16(tmem_d + (uint32_t)(buf * kBlk), ad, bd, idesc, (cc > 0 || j > 0) ? 1u : 0u);
           }
-          umma_commit(&sm.a_done[sa]);
-          umma_commit(&sm.b_done[sb]);
-          if (cc == n_chunks - 1) umma_commit(&sm.acc_done);
+          umma_commit(&sm.a_empty[sa]);
+          umma_commit(&sm.b_empty[sb]);
+          if (++sa == kAStages) sa = 0;
+          if (++sb == kBStages) sb = 0;
         }
-        if (++sa == kAStages) sa = 0;
-        if (++sb == kBStages) sb = 0;
+        umma_commit(&sm.acc_full[buf]);
       }
-      // diagonal block as fp32, transposed: jblk[i][i'] = J[i0 + i', i0 + i] (what a flip of site i adds to the
-      // field of i')
+    }
+  } else {
+    // ===================== epilogue: fields out of TMEM, sequential update of the block ================
+    const int row = tid - 4 * 32;                        // TMEM lane = chain within the tile
+    const int chain = blockIdx.x * kChains + row;
+    const bool chain_ok = chain < P.n_chains;
+    const uint32_t tmem_lane = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+    const float T = P.T_chain ? (float)P.T_chain[chain_ok ? chain : 0] : P.T;
+    const float invT = 1.0f / T;
+    const uint32_t chain_g = P.chain0 + (uint32_t)chain;
+    uint32_t accf_phase = 0;
+    // diagonal block J[blk, blk]: 8 bf16 per thread (row i0 + row/4, columns i0 + 8 (row%4) ..), fetched one
+    // block ahead so that the load latency hides behind the previous block's update
+    auto load_diag = [&](int blk) {
+      const int i0 = blk * kBlk;
+      return __ldg(reinterpret_cast<const uint4*>(P.J + (size_t)(i0 + (row >> 2)) * N + i0 + 8 * (row & 3)));
+    };
+    uint4 jd = load_diag(0);
+    for (int gb = 0; gb < total_blocks; ++gb) {
+      const int blk = gb % n_blocks, sweep = gb / n_blocks, buf = gb & 1;
+      const int i0 = blk * kBlk;
+      // diagonal block as fp32, transposed: jblk[i][i'] = J[i0 + i', i0 + i]
+      named_bar_sync(1, kChains);  // everybody is done with the previous block's jblk
       {
         const uint32_t jw[4] = {jd.x, jd.y, jd.z, jd.w};
-        const int r = tid >> 2, c0 = 8 * (tid & 3);
+        const int r = row >> 2, c0 = 8 * (row & 3);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          sm.jblk[c0 + 2 * e][r] = __uint_as_float(jw[e] << 16);              // bf16 -> fp32 is a 16-bit shift
+          sm.jblk[c0 + 2 * e][r] = __uint_as_float(jw[e] << 16);  // bf16 -> fp32 is a 16-bit shift
           sm.jblk[c0 + 2 * e + 1][r] = __uint_as_float(jw[e] & 0xffff0000u);
         }
       }
-      __syncthreads();
-      // ---- epilogue: fields out of TMEM, sequential update of the block -------------------------
-      mbar_wait(&sm.acc_done, acc_phase);
-      acc_phase ^= 1u;
+      if (gb + 1 < total_blocks) jd = load_diag((gb + 1) % n_blocks);
+      named_bar_sync(1, kChains);
+      mbar_wait(&sm.acc_full[buf], (accf_phase >> buf) & 1u);
+      accf_phase ^= 1u << buf;
       tc_fence_after();
       float h[kBlk];
-      tmem_ld32(tmem_lane + 0, h);
-      if (kBlk > 32) tmem_ld32(tmem_lane + 32, h + 32);
+      tmem_ld32(tmem_lane + (uint32_t)(buf * kBlk), h);
       tc_fence_before();
+      mbar_arrive(&sm.acc_free[buf]);  // the tensor core may overwrite this buffer (block gb + 2)
       if (P.bias) {
 #pragma unroll
         for (int i = 0; i < kBlk; ++i) h[i] += __ldg(P.bias + i0 + i);
       }
-      if (P.fields_out && chain_ok && P.gemm_only) {  // fields as accumulated by the tensor core
+      if (P.gemm_only) {
+        if (P.fields_out && chain_ok) {
 #pragma unroll
-        for (int i = 0; i < kBlk; ++i) P.fields_out[(size_t)chain * N + i0 + i] = h[i];
-      }
-      if (!P.gemm_only) {
-        // sequential heat-bath update of the 64 sites of this block for this thread's chain (gibbs.py:153-160)
+          for (int i = 0; i < kBlk; ++i) P.fields_out[(size_t)chain * N + i0 + i] = h[i];
+        }
+      } else {
+        // sequential heat-bath update of the 32 sites of this block for this thread's chain (gibbs.py:153-160)
         static_assert(kBlk == 32, "one state word per block");
-        uint32_t w[1] = {sm.sbits[blk][tid]};
-        const uint32_t chain_g = P.chain0 + (uint32_t)chain;
+        uint32_t w = sm.sbits[blk][row];
         tsu_u32x4 o = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int i = 0; i < kBlk; ++i) {
@@ -305,40 +353,40 @@ __global__ void __launch_bounds__(128, 1) dense_tc_kernel(TcParams P) {
             o = tsu_philox4x32_10((uint32_t)((i0 + i) >> 2), chain_g, P.sweep0 + (uint32_t)sweep, TSU_STREAM_DENSE_TC,
                                   P.k0, P.k1);
           const uint32_t r32 = (i & 3) == 0 ? o.x : ((i & 3) == 1 ? o.y : ((i & 3) == 2 ? o.z : o.w));
-          const float u = (float)(r32 >> 8) * (1.0f / 16777216.0f);   // 24-bit uniform, exact in fp32
+          const float u = (float)(r32 >> 8) * (1.0f / 16777216.0f);  // 24-bit uniform, exact in fp32
           if (P.fields_out && chain_ok) P.fields_out[(size_t)chain * N + i0 + i] = h[i];  // field at visit time
           const float x = h[i] * invT;
-          float pacc = 1.0f / (1.0f + __expf(-x));                     // gibbs.py:61-77 incl. the clamp
+          float pacc = 1.0f / (1.0f + __expf(-x));                    // gibbs.py:61-77 incl. the clamp
           pacc = x > 20.0f ? 1.0f : (x < -20.0f ? 0.0f : pacc);
-          const uint32_t nb = u < pacc ? 1u : 0u;                      // gibbs.py:126 (strict <)
-          const uint32_t ob = (w[i >> 5] >> (i & 31)) & 1u;
+          const uint32_t nb = u < pacc ? 1u : 0u;                     // gibbs.py:126 (strict <)
+          const uint32_t ob = (w >> i) & 1u;
           const float delta = (float)nb - (float)ob;
-          w[i >> 5] = (w[i >> 5] & ~(1u << (i & 31))) | (nb << (i & 31));
+          w = (w & ~(1u << i)) | (nb << i);
           // not yet visited sites of the block see the new value (rank-1 correction, branch free)
 #pragma unroll
           for (int ip = i + 1; ip < kBlk; ++ip) h[ip] = fmaf(sm.jblk[i][ip], delta, h[ip]);
         }
-        sm.sbits[blk][tid] = w[0];
+        sm.sbits[blk][row] = w;
       }
-      __syncthreads();  // jblk reuse, sbits of this block final before the next block's last chunk
+      mbar_arrive(&sm.state_ready);  // release: the producers may expand chunks holding this block
     }
-  }
-  if (!P.gemm_only && chain_ok) {  // unpack the final bits of this chain
-    for (int w = 0; w < N / 32; ++w) {
-      const uint32_t x = sm.sbits[w][tid];
-      uint8_t* dst = P.state + (size_t)chain * N + 32 * w;
+    if (!P.gemm_only && chain_ok) {  // unpack the final bits of this chain
+      for (int w = 0; w < N / 32; ++w) {
+        const uint32_t x = sm.sbits[w][row];
+        uint8_t* dst = P.state + (size_t)chain * N + 32 * w;
 #pragma unroll
-      for (int b = 0; b < 32; b += 4) {
-        const uint32_t n4 = (x >> b) & 15u;
-        *reinterpret_cast<uint32_t*>(dst + b) = (n4 & 1u) | ((n4 & 2u) << 7) | ((n4 & 4u) << 14) | ((n4 & 8u) << 21);
+        for (int b = 0; b < 32; b += 4) {
+          const uint32_t n4 = (x >> b) & 15u;
+          *reinterpret_cast<uint32_t*>(dst + b) = (n4 & 1u) | ((n4 & 2u) << 7) | ((n4 & 4u) << 14) | ((n4 & 8u) << 21);
+        }
       }
     }
   }
   // ---- teardown ----------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem_d) : "memory");
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem_d) : "memory");
   }
 }
 
@@ -348,7 +396,7 @@ static int launch_tc(const TcParams& P, cudaStream_t st) {
   const size_t smem = sizeof(TcSmem);
   cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  dense_tc_kernel<<<(P.n_chains + kChains - 1) / kChains, 128, smem, st>>>(P);
+  dense_tc_kernel<<<(P.n_chains + kChains - 1) / kChains, kThreads, smem, st>>>(P);
   e = cudaGetLastError();
   return e == cudaSuccess ? TSU_OK : (int)e;
 }
@@ -356,7 +404,7 @@ static int launch_tc(const TcParams& P, cudaStream_t st) {
 extern "C" int tsu_dense_gibbs_tc_run(const void* d_J_bf16, const float* d_bias, uint8_t* d_state, int n_chains, int N,
                                       double T, const double* d_T_chain, int n_sweeps, uint64_t seed, uint32_t sweep0,
                                       uint32_t chain0, float* d_fields_or_null, uintptr_t stream) {
-  TSU_CHECK_ARG(d_J_bf16 && d_state && n_chains > 0 && N > 0 && N % 64 == 0 && N <= 4096 && n_sweeps >= 0);
+  TSU_CHECK_ARG(d_J_bf16 && d_state && n_chains > 0 && N > 0 && N % 128 == 0 && N <= 4096 && n_sweeps >= 0);
   TSU_CHECK_ARG(d_T_chain || T > 0);
   TcParams P = {};
   P.J = reinterpret_cast<const __nv_bfloat16*>(d_J_bf16);
@@ -378,7 +426,7 @@ extern "C" int tsu_dense_gibbs_tc_run(const void* d_J_bf16, const float* d_bias,
 
 extern "C" int tsu_dense_tc_debug_fields(const void* d_J_bf16, const uint8_t* d_state, int n_chains, int N,
                                          float* d_fields, uintptr_t stream) {
-  TSU_CHECK_ARG(d_J_bf16 && d_state && d_fields && n_chains > 0 && N > 0 && N % 64 == 0 && N <= 4096);
+  TSU_CHECK_ARG(d_J_bf16 && d_state && d_fields && n_chains > 0 && N > 0 && N % 128 == 0 && N <= 4096);
   TcParams P = {};
   P.J = reinterpret_cast<const __nv_bfloat16*>(d_J_bf16);
   P.state = const_cast<uint8_t*>(d_state);

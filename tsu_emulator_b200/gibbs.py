@@ -233,8 +233,8 @@ class GibbsSampler:
         device = self._dev()
         J = _as_square(coupling)
         N = J.shape[0]
-        if N % 64 or N > 4096:
-            raise ValueError("the tensor-core path needs N % 64 == 0 and N <= 4096")
+        if N % 128 or N > 4096:
+            raise ValueError("the tensor-core path needs N % 128 == 0 and N <= 4096")
         if self.config.update_order != "sequential":
             raise ValueError("the tensor-core path implements the sequential update order")
         Jd = torch.from_numpy(np.ascontiguousarray(J)).to(device=device, dtype=torch.bfloat16).contiguous()
