@@ -13,8 +13,10 @@
 // sites of the block, which makes the result identical to a site-by-site sweep with the same fields.
 //
 // One CTA owns 128 chains (TMEM lane = chain).  The chain states stay resident in shared memory as bits
-// for the whole sweep (64 KB); each K-chunk of 64 sites is expanded to a bf16 operand tile in the
-// canonical no-swizzle K-major UMMA layout, the matching J tile is streamed from L2 with cp.async.
+// for the whole sweep (64 KB).  Each K-chunk of 128 sites is expanded to bf16 0/1 by the thread that owns
+// the chain and written straight into TENSOR MEMORY (tcgen05.st, lane = chain, column = K pair): the spin
+// operand A never touches shared memory, so no generic->async proxy fence and no smem bandwidth is spent
+// on it.  The matching J tile (operand B, K-major, no swizzle) is streamed from L2 with cp.async.
 
 #include <cuda_bf16.h>
 
@@ -26,9 +28,11 @@ namespace {
 constexpr int kChains = 128;  // chains per CTA = UMMA M = TMEM lanes
 constexpr int kBlk = 32;      // sites per block = UMMA N
 constexpr int kKC = 128;      // K-chunk (sites) per pipeline stage
-constexpr int kAStages = 3;   // expanded spin tiles (32 KB each)
-constexpr int kBStages = 6;   // J tile ring (8 KB each)
-constexpr int kLook = 4;      // J tiles are requested 4 chunks (512 sites) ahead of their use
+constexpr int kAStages = 6;   // expanded spin tiles in tensor memory (64 columns each)
+constexpr int kAccCols = 64;  // two 32-column fp32 accumulator buffers
+constexpr int kTmemCols = 512;  // 64 accumulator + 6 x 64 operand columns
+constexpr int kBStages = 12;  // J tile ring (8 KB each)
+constexpr int kLook = 6;      // J tiles are requested 6 chunks (768 sites) ahead of their use
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -55,6 +59,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
       :
       : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// same with the A operand in tensor memory (lane = row, one 32-bit column = two consecutive K elements)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+
+// 16 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 
@@ -124,13 +150,12 @@ struct TcParams {
 
 constexpr int kThreads = 288;  // warps 0-3 producers, 4-7 epilogue (chain = lane of TMEM), 8 MMA issuer
 
-// shared memory carve-up (217 KB)
+// shared memory carve-up (~120 KB)
 struct TcSmem {
   uint32_t sbits[4096 / 32][kChains];                                     // chain states, word-major: sbits[w][chain]
-  __align__(128) __nv_bfloat16 a[kAStages][kKC / 8][kChains / 8][8][8];   // [k16B][row group][row][8 elems]
   __align__(128) __nv_bfloat16 b[kBStages][kKC / 8][kBlk / 8][8][8];
   __align__(16) float jblk[kBlk][kBlk + 4];  // J[blk, blk] as fp32, transposed: jblk[i][i'] = J[i0+i'][i0+i]
-  __align__(16) uint4 lut[256];              // byte -> 8 bf16 (0.0 / 1.0)
+  __align__(128) uint2 lut[16];              // nibble -> 4 bf16 (0.0 / 1.0); 16 x 8 B = one bank sweep: conflict free
   __align__(8) uint64_t full[kAStages];      // producers -> MMA: A stage written, J tile landed      (count 128)
   __align__(8) uint64_t a_empty[kAStages];   // MMA -> producers: the MMAs that read the A stage are done (commit)
   __align__(8) uint64_t b_empty[kBStages];   // MMA -> producers: J ring slot free                       (commit)
@@ -157,11 +182,11 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
   static_assert(kKC == 4 * kBlk, "a K-chunk holds four blocks");
 
   // ---- one-time setup -------------------------------------------------------------------------
-  for (int i = tid; i < 256; i += kThreads) {
-    uint32_t w[4];
+  if (tid < 16) {
+    uint32_t w[2];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) w[p] = ((i >> (2 * p)) & 1 ? 0x3F80u : 0u) | ((i >> (2 * p + 1)) & 1 ? 0x3F800000u : 0u);
-    sm.lut[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    for (int p = 0; p < 2; ++p) w[p] = ((tid >> (2 * p)) & 1 ? 0x3F80u : 0u) | ((tid >> (2 * p + 1)) & 1 ? 0x3F800000u : 0u);
+    sm.lut[tid] = make_uint2(w[0], w[1]);
   }
   if (tid < kChains) {  // pack this chain's bits
     const int chain = blockIdx.x * kChains + tid;
@@ -192,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(&sm.tmem_base)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm.tmem_base)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -250,15 +275,24 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
           mbar_wait(&sm.a_empty[sa], (a_phase >> sa) & 1u);
           a_phase ^= 1u << sa;
         }
+        // 128 bits of this chain -> 64 packed bf16 pairs -> 64 TMEM columns of the chain's lane
+        const uint32_t a_col = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(kAccCols + sa * (kKC / 2));
 #pragma unroll
         for (int q = 0; q < kKC / 32; ++q) {
           const uint32_t w = sm.sbits[(kKC / 32) * kc + q][tid];
+          uint32_t r[16];
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)
-            *reinterpret_cast<uint4*>(&sm.a[sa][4 * q + k4][tid >> 3][tid & 7][0]) = sm.lut[(w >> (8 * k4)) & 0xFFu];
+          for (int nb = 0; nb < 8; ++nb) {
+            const uint2 e = sm.lut[(w >> (4 * nb)) & 15u];
+            r[2 * nb] = e.x;
+            r[2 * nb + 1] = e.y;
+          }
+          tmem_st16(a_col + 16 * q, r);
         }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         cp_async_wait<kLook>();  // this thread's pieces of the J tile of chunk g have landed
-        fence_async_smem();      // generic-proxy writes -> visible to the tensor core (async proxy)
+        fence_async_smem();      // cp.async writes -> visible to the tensor core (async proxy)
+        tc_fence_before();
         mbar_arrive(&sm.full[sa]);
         if (++sa == kAStages) sa = 0;
       }
@@ -281,9 +315,9 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
           tc_fence_after();
 #pragma unroll
           for (int j = 0; j < kKC / 16; ++j) {
-            const uint64_t ad = umma_desc(smem_u32(&sm.a[sa][2 * j][0][0][0]), (kChains / 8) * 128, 128);
             const uint64_t bd = umma_desc(smem_u32(&sm.b[sb][2 * j][0][0][0]), (kBlk / 8) * 128, 128);
-            umma_bf16(tmem_d + (uint32_t)(buf * kBlk), ad, bd, idesc, (cc > 0 || j > 0) ? 1u : 0u);
+            umma_bf16_ts(tmem_d + (uint32_t)(buf * kBlk), tmem_d + (uint32_t)(kAccCols + sa * (kKC / 2) + 8 * j), bd, idesc,
+                         (cc > 0 || j > 0) ? 1u : 0u);
           }
           umma_commit(&sm.a_empty[sa]);
           umma_commit(&sm.b_empty[sb]);
@@ -386,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
   tc_fence_before();
   __syncthreads();
   if (warp == 8) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem_d) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_d) : "memory");
   }
 }
 
