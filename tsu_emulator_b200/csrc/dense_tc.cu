@@ -28,11 +28,12 @@ namespace {
 constexpr int kChains = 128;  // chains per CTA = UMMA M = TMEM lanes
 constexpr int kBlk = 32;      // sites per block = UMMA N
 constexpr int kKC = 128;      // K-chunk (sites) per pipeline stage
-constexpr int kAStages = 6;   // expanded spin tiles in tensor memory (64 columns each)
-constexpr int kAccCols = 64;  // two 32-column fp32 accumulator buffers
-constexpr int kTmemCols = 512;  // 64 accumulator + 6 x 64 operand columns
-constexpr int kBStages = 12;  // J tile ring (8 KB each)
-constexpr int kLook = 6;      // J tiles are requested 6 chunks (768 sites) ahead of their use
+constexpr int kAStages = 4;   // expanded spin tiles in tensor memory (64 columns each)
+constexpr int kPartials = 4;  // independent partial accumulators: consecutive MMAs never wait on each other's result
+constexpr int kAccCols = 2 * kPartials * kBlk;  // two buffers x 4 partial 32-column fp32 accumulators = 256 columns
+// tensor memory: 256 accumulator + 4 x 64 operand columns = 512 columns
+constexpr int kBStages = 14;  // J tile ring (8 KB each); every producer group owns kBStages / kGroups slots
+constexpr int kLook = 5;      // a group requests J tiles 5 of its own chunks ahead (must be < slots per group)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -84,6 +85,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -104,6 +111,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
   } while (!done);
+}
+
+// for long waits (the epilogue idles for a whole block's GEMM): back off so that the polling does not compete
+// with the producers for shared-memory / issue bandwidth
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(256);
+  }
 }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -148,20 +172,24 @@ struct TcParams {
   int gemm_only;            // diagnostics: no spin update (fields of the initial state for every site)
 };
 
-constexpr int kThreads = 288;  // warps 0-3 producers, 4-7 epilogue (chain = lane of TMEM), 8 MMA issuer
+constexpr int kGroups = 2;        // producer groups: group q expands the K-chunks with (chunk index % kGroups) == q,
+                                 // so the per-chunk latencies (TMEM store, fences, barrier wake-ups) of the groups overlap
+constexpr int kProducers = 128 * kGroups;  // warps 0-7: 4 warps (128 chains) per group
+constexpr int kThreads = 416;    // + warps 8-11 epilogue (thread = chain = TMEM lane) + warp 12 MMA issuer
 
 // shared memory carve-up (~120 KB)
 struct TcSmem {
   uint32_t sbits[4096 / 32][kChains];                                     // chain states, word-major: sbits[w][chain]
   __align__(128) __nv_bfloat16 b[kBStages][kKC / 8][kBlk / 8][8][8];
   __align__(16) float jblk[kBlk][kBlk + 4];  // J[blk, blk] as fp32, transposed: jblk[i][i'] = J[i0+i'][i0+i]
-  __align__(128) uint2 lut[16];              // nibble -> 4 bf16 (0.0 / 1.0); 16 x 8 B = one bank sweep: conflict free
+  __align__(128) uint4 lut[256][8];          // byte -> 8 bf16 (0.0 / 1.0), one copy per lane%8: a quarter-warp LDS.128
+                                             // touches 8 different 16-byte bank groups whatever the bytes are
   __align__(8) uint64_t full[kAStages];      // producers -> MMA: A stage written, J tile landed      (count 128)
   __align__(8) uint64_t a_empty[kAStages];   // MMA -> producers: the MMAs that read the A stage are done (commit)
   __align__(8) uint64_t b_empty[kBStages];   // MMA -> producers: J ring slot free                       (commit)
   __align__(8) uint64_t acc_full[2];         // MMA -> epilogue: accumulator buffer complete             (commit)
   __align__(8) uint64_t acc_free[2];         // epilogue -> MMA: accumulator buffer read out             (count 128)
-  __align__(8) uint64_t state_ready;         // epilogue -> producers: bits of the block written         (count 128)
+  __align__(8) uint64_t state_ready[4];      // epilogue -> producers: bits of block gb written (ring, count 128)
   uint32_t tmem_base;
 };
 
@@ -182,11 +210,13 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
   static_assert(kKC == 4 * kBlk, "a K-chunk holds four blocks");
 
   // ---- one-time setup -------------------------------------------------------------------------
-  if (tid < 16) {
-    uint32_t w[2];
+  for (int i = tid; i < 256 * 8; i += kThreads) {
+    const int byte = i >> 3;
+    uint32_t w[4];
 #pragma unroll
-    for (int p = 0; p < 2; ++p) w[p] = ((tid >> (2 * p)) & 1 ? 0x3F80u : 0u) | ((tid >> (2 * p + 1)) & 1 ? 0x3F800000u : 0u);
-    sm.lut[tid] = make_uint2(w[0], w[1]);
+    for (int p = 0; p < 4; ++p)
+      w[p] = ((byte >> (2 * p)) & 1 ? 0x3F80u : 0u) | ((byte >> (2 * p + 1)) & 1 ? 0x3F800000u : 0u);
+    sm.lut[byte][i & 7] = make_uint4(w[0], w[1], w[2], w[3]);
   }
   if (tid < kChains) {  // pack this chain's bits
     const int chain = blockIdx.x * kChains + tid;
@@ -213,10 +243,10 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
       mbar_init(&sm.acc_full[s], 1);
       mbar_init(&sm.acc_free[s], kChains);
     }
-    mbar_init(&sm.state_ready, kChains);
+    for (int s = 0; s < 4; ++s) mbar_init(&sm.state_ready[s], kChains);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == 12) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm.tmem_base)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -225,25 +255,17 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
   tc_fence_after();
   const uint32_t tmem_d = sm.tmem_base;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ===================== producers: expand spins to bf16 A tiles, stream J tiles ======================
-    uint32_t a_phase = 0, b_phase = 0, ready_phase = 0;
+    // group = warp / 4 handles every kGroups-th chunk; inside a group, thread = chain (TMEM lane)
+    const int group = warp >> 2, row = tid & (kChains - 1);
+    uint32_t a_phase = 0, b_phase = 0;
+    int ready_seen = 0;  // number of state_ready phases consumed (block gb needs gb of them for its last two chunks)
+    // J tile requests run kLook of the group's own chunks ahead (across blocks and sweeps)
     int ld_sweep = 0, ld_blk = 0, ld_cc = 0, ld_stage = 0;
     long long ld_count = 0;
-    auto load_b = [&]() {  // J tile request, kLook chunks ahead of consumption (across blocks and sweeps)
-      if (ld_sweep < P.n_sweeps) {
-        int lkc = ld_cc + (ld_blk >> 2) + 1;
-        if (lkc >= n_chunks) lkc -= n_chunks;
-        if (ld_count >= kBStages) {
-          mbar_wait(&sm.b_empty[ld_stage], (b_phase >> ld_stage) & 1u);
-          b_phase ^= 1u << ld_stage;
-        }
-#pragma unroll
-        for (int p = 0; p < kBlk * (kKC / 8) / kChains; ++p) {
-          const int piece = tid + kChains * p;
-          const int n = piece / (kKC / 8), k16 = piece % (kKC / 8);
-          cp_async16(&sm.b[ld_stage][k16][n >> 3][n & 7][0], P.J + (size_t)(ld_blk * kBlk + n) * N + lkc * kKC + 8 * k16);
-        }
+    auto ld_advance = [&](int n) {  // skip n chunks of the global sequence
+      for (int i = 0; i < n; ++i) {
         ++ld_count;
         if (++ld_stage == kBStages) ld_stage = 0;
         if (++ld_cc == n_chunks) {
@@ -254,53 +276,80 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
           }
         }
       }
+    };
+    auto load_b = [&]() {
+      if (ld_sweep < P.n_sweeps) {
+        int lkc = ld_cc + (ld_blk >> 2) + 1;
+        if (lkc >= n_chunks) lkc -= n_chunks;
+        if (ld_count >= kBStages) {
+          mbar_wait(&sm.b_empty[ld_stage], (b_phase >> ld_stage) & 1u);
+          b_phase ^= 1u << ld_stage;
+        }
+#pragma unroll
+        for (int p = 0; p < kBlk * (kKC / 8) / kChains; ++p) {
+          const int piece = row + kChains * p;
+          const int n = piece / (kKC / 8), k16 = piece % (kKC / 8);
+          cp_async16(&sm.b[ld_stage][k16][n >> 3][n & 7][0], P.J + (size_t)(ld_blk * kBlk + n) * N + lkc * kKC + 8 * k16);
+        }
+        ld_advance(kGroups);
+      }
       cp_async_commit();  // (an empty group at the tail keeps the group count uniform)
     };
+    static_assert(kBStages % kGroups == 0 && kAStages % kGroups == 0 && kLook < kBStages / kGroups, "ring ownership");
+    ld_advance(group);                       // first chunk of this group
     for (int i = 0; i < kLook; ++i) load_b();
     long long g = 0;
     int sa = 0;
     for (int gb = 0; gb < total_blocks; ++gb) {
       const int blk = gb % n_blocks;
       for (int cc = 0; cc < n_chunks; ++cc, ++g) {
-        // chunk order: own + 1, ..., own - 1, own.  The two last chunks may hold the previous block's sites,
-        // so they wait for that block's update; everything earlier only needs older state.
-        int kc = cc + (blk >> 2) + 1;
-        if (kc >= n_chunks) kc -= n_chunks;
-        load_b();
-        if (gb > 0 && cc == (n_chunks >= 2 ? n_chunks - 2 : 0)) {
-          mbar_wait(&sm.state_ready, ready_phase);
-          ready_phase ^= 1u;
-        }
-        if (g >= kAStages) {
-          mbar_wait(&sm.a_empty[sa], (a_phase >> sa) & 1u);
-          a_phase ^= 1u << sa;
-        }
-        // 128 bits of this chain -> 64 packed bf16 pairs -> 64 TMEM columns of the chain's lane
-        const uint32_t a_col = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(kAccCols + sa * (kKC / 2));
-#pragma unroll
-        for (int q = 0; q < kKC / 32; ++q) {
-          const uint32_t w = sm.sbits[(kKC / 32) * kc + q][tid];
-          uint32_t r[16];
-#pragma unroll
-          for (int nb = 0; nb < 8; ++nb) {
-            const uint2 e = sm.lut[(w >> (4 * nb)) & 15u];
-            r[2 * nb] = e.x;
-            r[2 * nb + 1] = e.y;
+        if ((int)(g % kGroups) == group) {
+          // chunk order: own + 1, ..., own - 1, own.  The two last chunks may hold the previous block's sites,
+          // so they wait for that block's update; everything earlier only needs older state.
+          int kc = cc + (blk >> 2) + 1;
+          if (kc >= n_chunks) kc -= n_chunks;
+          load_b();
+          const int need = (cc >= n_chunks - 2) ? gb : gb - 1;
+          while (ready_seen < need) {
+            mbar_wait(&sm.state_ready[ready_seen & 3], (uint32_t)((ready_seen >> 2) & 1));
+            ++ready_seen;
           }
-          tmem_st16(a_col + 16 * q, r);
+          if (g >= kAStages) {
+            mbar_wait(&sm.a_empty[sa], (a_phase >> sa) & 1u);
+            a_phase ^= 1u << sa;
+          }
+          // 128 bits of this chain -> 64 packed bf16 pairs -> 64 TMEM columns of the chain's lane
+          const uint32_t a_col = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kAccCols + sa * (kKC / 2));
+#pragma unroll
+          for (int q = 0; q < kKC / 32; ++q) {
+            const uint32_t w = sm.sbits[(kKC / 32) * kc + q][row];
+            uint32_t r[16];
+#pragma unroll
+            for (int by = 0; by < 4; ++by) {
+              const uint4 e = sm.lut[(w >> (8 * by)) & 0xFFu][tid & 7];
+              r[4 * by] = e.x; r[4 * by + 1] = e.y; r[4 * by + 2] = e.z; r[4 * by + 3] = e.w;
+            }
+            tmem_st16(a_col + 16 * q, r);
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          cp_async_wait<kLook>();  // this thread's pieces of the J tile of this chunk have landed
+          fence_async_smem();      // cp.async writes -> visible to the tensor core (async proxy)
+          tc_fence_before();
+          mbar_arrive(&sm.full[sa]);
         }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        cp_async_wait<kLook>();  // this thread's pieces of the J tile of chunk g have landed
-        fence_async_smem();      // cp.async writes -> visible to the tensor core (async proxy)
-        tc_fence_before();
-        mbar_arrive(&sm.full[sa]);
         if (++sa == kAStages) sa = 0;
       }
     }
-  } else if (warp == 8) {
-    // ===================== MMA issuer: one thread feeds the tensor core ===============================
-    if ((tid & 31) == 0) {
+  } else if (warp == 12) {
+    // ===================== MMA issuer: one elected lane feeds the tensor core ===========================
+    // The whole warp runs the loop (uniform control flow keeps counters and descriptors in uniform registers);
+    // only the tcgen05.mma / commit instructions are issued by the elected lane.
+    {
       const uint32_t idesc = umma_idesc(kChains, kBlk);
+      constexpr uint32_t kLbo = (kBlk / 8) * 128, kSbo = 128;
+      const uint64_t b_desc0 = umma_desc(smem_u32(&sm.b[0][0][0][0][0]), kLbo, kSbo);
+      constexpr uint32_t kStageUnits = (uint32_t)(sizeof(sm.b[0]) >> 4);   // 16-byte units per ring slot
+      constexpr uint32_t kStepUnits = (2 * kLbo) >> 4;                      // per K = 16 step
       uint32_t full_phase = 0, free_phase = 0;
       int sa = 0, sb = 0;
       for (int gb = 0; gb < total_blocks; ++gb) {
@@ -313,23 +362,29 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
           mbar_wait(&sm.full[sa], (full_phase >> sa) & 1u);
           full_phase ^= 1u << sa;
           tc_fence_after();
+          if (elect_one()) {
+            const uint64_t bd0 = b_desc0 + (uint64_t)((uint32_t)sb * kStageUnits);
+            const uint32_t a0 = tmem_d + (uint32_t)(kAccCols + sa * (kKC / 2));
+            const uint32_t d0 = tmem_d + (uint32_t)(buf * kPartials * kBlk);
 #pragma unroll
-          for (int j = 0; j < kKC / 16; ++j) {
-            const uint64_t bd = umma_desc(smem_u32(&sm.b[sb][2 * j][0][0][0]), (kBlk / 8) * 128, 128);
-            umma_bf16_ts(tmem_d + (uint32_t)(buf * kBlk), tmem_d + (uint32_t)(kAccCols + sa * (kKC / 2) + 8 * j), bd, idesc,
-                         (cc > 0 || j > 0) ? 1u : 0u);
+            for (int j = 0; j < kKC / 16; ++j) {
+              // K-steps rotate over kPartials accumulators; the epilogue adds them up
+              umma_bf16_ts(d0 + (uint32_t)((j % kPartials) * kBlk), a0 + 8u * j, bd0 + (uint64_t)(j * kStepUnits), idesc,
+                           (cc > 0 || j >= kPartials) ? 1u : 0u);
+            }
+            umma_commit(&sm.a_empty[sa]);
+            umma_commit(&sm.b_empty[sb]);
+            if (cc == n_chunks - 1) umma_commit(&sm.acc_full[buf]);
           }
-          umma_commit(&sm.a_empty[sa]);
-          umma_commit(&sm.b_empty[sb]);
+          __syncwarp();
           if (++sa == kAStages) sa = 0;
           if (++sb == kBStages) sb = 0;
         }
-        umma_commit(&sm.acc_full[buf]);
       }
     }
   } else {
     // ===================== epilogue: fields out of TMEM, sequential update of the block ================
-    const int row = tid - 4 * 32;                        // TMEM lane = chain within the tile
+    const int row = tid - kProducers;                    // TMEM lane = chain within the tile
     const int chain = blockIdx.x * kChains + row;
     const bool chain_ok = chain < P.n_chains;
     const uint32_t tmem_lane = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
@@ -360,11 +415,18 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
       }
       if (gb + 1 < total_blocks) jd = load_diag((gb + 1) % n_blocks);
       named_bar_sync(1, kChains);
-      mbar_wait(&sm.acc_full[buf], (accf_phase >> buf) & 1u);
+      mbar_wait_backoff(&sm.acc_full[buf], (accf_phase >> buf) & 1u);
       accf_phase ^= 1u << buf;
       tc_fence_after();
       float h[kBlk];
-      tmem_ld32(tmem_lane + (uint32_t)(buf * kBlk), h);
+      tmem_ld32(tmem_lane + (uint32_t)(buf * kPartials * kBlk), h);
+#pragma unroll
+      for (int pp = 1; pp < kPartials; ++pp) {
+        float hp[kBlk];
+        tmem_ld32(tmem_lane + (uint32_t)((buf * kPartials + pp) * kBlk), hp);
+#pragma unroll
+        for (int i = 0; i < kBlk; ++i) h[i] += hp[i];
+      }
       tc_fence_before();
       mbar_arrive(&sm.acc_free[buf]);  // the tensor core may overwrite this buffer (block gb + 2)
       if (P.bias) {
@@ -402,7 +464,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
         }
         sm.sbits[blk][row] = w;
       }
-      mbar_arrive(&sm.state_ready);  // release: the producers may expand chunks holding this block
+      mbar_arrive(&sm.state_ready[gb & 3]);  // release: the producers may expand chunks holding this block
     }
     if (!P.gemm_only && chain_ok) {  // unpack the final bits of this chain
       for (int w = 0; w < N / 32; ++w) {
@@ -419,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
   // ---- teardown ----------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_d) : "memory");
   }
 }
