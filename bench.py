@@ -303,8 +303,8 @@ def run_b200_arm(args):
         e2e = {
             "value": world * updates_per_step * args.steps / (e2e_ms * 1e-3),
             "unit": UNIT,
-            "h2d_bytes_per_step": int(state_bytes),
-            "d2h_bytes_per_step": int(n_rep * 16),
+            "h2d_bytes_per_step": int(state_bytes) * world,
+            "d2h_bytes_per_step": int(n_rep * 16) * world,
             "ms_per_step": e2e_ms / args.steps,
             "api": "Ising2DEngine: pinned host state -> H2D (16 chunks, overlapped) -> sweep(10) -> observables -> D2H",
             "pinned_host_bytes": int(host.numel() * 4),

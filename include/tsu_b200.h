@@ -94,6 +94,22 @@ int tsu_ising2d_sweeps(uint32_t* d_state, int n_replicas, int rows, int cols, in
                        int wrap_cols, const uint32_t* d_lut, const int32_t* d_lut_index,
                        uint64_t seed, uint32_t sweep0, int n_sweeps, uint32_t replica0,
                        uintptr_t stream);
+/* Run-time specialisation (NVRTC) of the fast half-sweep kernel for ONE threshold table (all replicas at the
+ * same temperature): the eight 5-bit truth tables of h_lut (host copy of the table, layout above) become
+ * literals of csrc/ising2d_fast.cuh, which removes the jump tables from the inner loop (+17 % measured).
+ * src_dir = directory that holds ising2d_fast.cuh and philox.cuh.  Returns a handle >= 1, or 0 when NVRTC /
+ * the driver API is unavailable or compilation failed (log_buf gets the reason): callers then keep using the
+ * prebuilt kernels.  Results are bit-identical to tsu_ising2d_half_sweep / tsu_ising2d_sweeps; geometries
+ * outside the fast path silently use the prebuilt generic kernel. */
+int tsu_ising2d_jit_prepare(const uint32_t* h_lut, const char* src_dir, char* log_buf, int log_len);
+int tsu_ising2d_half_sweep_jit(int jit_handle, uint32_t* d_state, int n_replicas, int rows, int cols,
+                               int wrap_rows, int wrap_cols, int colour, const uint32_t* d_lut,
+                               uint64_t seed, uint32_t sweep, uint32_t replica0, int row0,
+                               const uint32_t* d_halo_top, const uint32_t* d_halo_bot, uintptr_t stream);
+int tsu_ising2d_sweeps_jit(int jit_handle, uint32_t* d_state, int n_replicas, int rows, int cols,
+                           int wrap_rows, int wrap_cols, const uint32_t* d_lut, uint64_t seed,
+                           uint32_t sweep0, int n_sweeps, uint32_t replica0, uintptr_t stream);
+
 /* Parity mode: same update, but the uniform of site (replica,row,col) is read from
  * d_uniforms[replica][row][col] (uint32 k meaning k/2^32) instead of Philox. */
 int tsu_ising2d_half_sweep_injected(uint32_t* d_state, int n_replicas, int rows, int cols,

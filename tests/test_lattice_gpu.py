@@ -166,3 +166,29 @@ def test_cold_lattice_stays_ordered_and_hot_disorders():
     eng.set_temperature(10.0)
     eng.sweep(50)
     assert abs(eng.magnetization()[0]) < 0.05
+
+
+def test_jit_specialised_and_prebuilt_kernels_agree(monkeypatch):
+    """the NVRTC table-specialised build of the fast kernel and the prebuilt jump-table kernel are the same function"""
+    import torch
+    rows, cols, seed = 64, 512, 31
+    a = make_engine(rows, cols, n_replicas=3, temperature=2.269, periodic=True, seed=seed)
+    if a._jit <= 0:
+        pytest.skip("NVRTC specialisation unavailable here: " + getattr(a, "_jit_log", ""))
+    monkeypatch.setenv("TSU_B200_NO_JIT", "1")
+    b = make_engine(rows, cols, n_replicas=3, temperature=2.269, periodic=True, seed=seed)
+    assert b._jit == 0
+    a.init_random().sweep(5)
+    b.init_random().sweep(5)
+    assert torch.equal(a.state, b.state)
+    want = O.checkerboard_sweeps_philox(O.init_bits(seed, 1, rows, cols), seed, 1, 0, 5, 1.0, 0.0, 2.269, True)
+    assert (a.get_spins(pm1=False)[1] == want).all()
+    # a second engine at the same temperature reuses the cached module; a new temperature compiles a new one
+    c = make_engine(rows, cols, temperature=2.269, periodic=True, seed=seed)
+    monkeypatch.delenv("TSU_B200_NO_JIT")
+    d = make_engine(rows, cols, temperature=2.269, periodic=True, seed=seed)
+    e = make_engine(rows, cols, temperature=0.1, periodic=True, seed=seed)   # p == 1.0 classes
+    assert d._jit == a._jit and e._jit > 0 and e._jit != a._jit
+    e.init_random().sweep(3)
+    want = O.checkerboard_sweeps_philox(O.init_bits(seed, 0, rows, cols), seed, 0, 0, 3, 1.0, 0.0, 0.1, True)
+    assert (e.get_spins(pm1=False)[0] == want).all()

@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtsu_b200.so")
+LIB_PATH = os.environ.get("TSU_B200_LIB") or os.path.join(_HERE, "libtsu_b200.so")
 
 c_uintptr = ctypes.c_size_t  # uintptr_t
 
@@ -49,6 +49,16 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_uint64, c_uint32, c_int, c_uint32,
          c_uintptr],
+    ),
+    "tsu_ising2d_jit_prepare": (c_int, [POINTER(c_uint32), c_char_p, c_char_p, c_int]),
+    "tsu_ising2d_half_sweep_jit": (
+        c_int,
+        [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_uint64, c_uint32, c_uint32, c_int,
+         c_void_p, c_void_p, c_uintptr],
+    ),
+    "tsu_ising2d_sweeps_jit": (
+        c_int,
+        [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_uint64, c_uint32, c_int, c_uint32, c_uintptr],
     ),
     "tsu_ising2d_half_sweep_injected": (
         c_int,

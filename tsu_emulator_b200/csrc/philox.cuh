@@ -8,7 +8,9 @@
 // One call = 10 rounds of { 2 x IMAD.WIDE.U32, 2 x LOP3 } : 20 fma-pipe + 20 alu-pipe
 // instructions for 128 random bits, all in registers.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#endif
 
 #define TSU_PHILOX_M0 0xD2511F53u
 #define TSU_PHILOX_M1 0xCD9E8D57u

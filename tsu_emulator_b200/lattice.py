@@ -140,6 +140,22 @@ class Ising2DEngine:
         else:
             self.lut_index = torch.from_numpy(inv.astype(np.int32)).to(self.device)
         self._lut_temps = uniq
+        self._jit = self._jit_prepare(luts[0]) if temps.size == 1 else 0
+
+    def _jit_prepare(self, lut_host: np.ndarray) -> int:
+        """table-specialised build of the fast kernel (0 = unavailable: the prebuilt kernels are used)"""
+        import ctypes
+        import os
+
+        if os.environ.get("TSU_B200_NO_JIT"):
+            return 0
+        src_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc").encode()
+        log = ctypes.create_string_buffer(4096)
+        arr = (ctypes.c_uint32 * LUT_WORDS)(*[int(x) for x in lut_host])
+        with self._torch.cuda.device(self.device):
+            handle = int(self.lib.tsu_ising2d_jit_prepare(arr, src_dir, log, 4096))
+        self._jit_log = log.value.decode(errors="replace")
+        return max(handle, 0)
 
     def set_temperature_tables(self, temperatures, lut_index):
         """one threshold table per entry of `temperatures` (kept in that order) and an explicit
@@ -151,6 +167,7 @@ class Ising2DEngine:
         luts = np.stack([build_lut(self.coupling, self.field, float(t), self.bias_mode) for t in temps])
         self.lut = torch.from_numpy(luts.view(np.int32)).to(self.device)
         self._lut_temps = temps
+        self._jit = 0
         self.set_lut_index(lut_index)
 
     def set_lut_index(self, lut_index):
@@ -222,7 +239,14 @@ class Ising2DEngine:
     def half_sweep(self, colour: int, halo_top=None, halo_bot=None, uniforms=None):
         """resample every site of `colour`; halos are [n_replicas, wpr] int32 rows of the other colour."""
         with self._torch.cuda.device(self.device):
-            if uniforms is None:
+            if uniforms is None and self.lut_index is None and getattr(self, "_jit", 0) > 0:
+                _lib.call(
+                    "tsu_ising2d_half_sweep_jit", self._jit, ptr(self.state), self.n_replicas, self.rows, self.cols,
+                    int(self.wrap_rows and not self.is_slab), int(self.wrap_cols), int(colour), ptr(self.lut),
+                    self.seed, self.sweep_index & 0xFFFFFFFF, self.replica0, self.row0, ptr(halo_top), ptr(halo_bot),
+                    _lib.current_stream(),
+                )
+            elif uniforms is None:
                 _lib.call(
                     "tsu_ising2d_half_sweep", ptr(self.state), self.n_replicas, self.rows, self.cols,
                     int(self.wrap_rows and not self.is_slab), int(self.wrap_cols), int(colour), ptr(self.lut),
@@ -242,11 +266,18 @@ class Ising2DEngine:
         if self.is_slab:
             raise RuntimeError("row-slab engines are driven by ShardedIsing2D (halo exchange between half-sweeps)")
         with self._torch.cuda.device(self.device):
-            _lib.call(
-                "tsu_ising2d_sweeps", ptr(self.state), self.n_replicas, self.rows, self.cols, int(self.wrap_rows),
-                int(self.wrap_cols), ptr(self.lut), ptr(self.lut_index), self.seed, self.sweep_index & 0xFFFFFFFF,
-                int(n_sweeps), self.replica0, _lib.current_stream(),
-            )
+            if self.lut_index is None and getattr(self, "_jit", 0) > 0:
+                _lib.call(
+                    "tsu_ising2d_sweeps_jit", self._jit, ptr(self.state), self.n_replicas, self.rows, self.cols,
+                    int(self.wrap_rows), int(self.wrap_cols), ptr(self.lut), self.seed, self.sweep_index & 0xFFFFFFFF,
+                    int(n_sweeps), self.replica0, _lib.current_stream(),
+                )
+            else:
+                _lib.call(
+                    "tsu_ising2d_sweeps", ptr(self.state), self.n_replicas, self.rows, self.cols, int(self.wrap_rows),
+                    int(self.wrap_cols), ptr(self.lut), ptr(self.lut_index), self.seed, self.sweep_index & 0xFFFFFFFF,
+                    int(n_sweeps), self.replica0, _lib.current_stream(),
+                )
         self.sweep_index += int(n_sweeps)
         return self
 
