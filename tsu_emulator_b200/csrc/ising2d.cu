@@ -655,9 +655,13 @@ int tsu_ising2d_jit_prepare(const uint32_t* h_lut, const char* src_dir, char* lo
   std::string src;
   for (int k = 0; k < 8; ++k) src += "#define TSU_FT" + std::to_string(k) + " " + std::to_string(tab[k]) + "\n";
   src += "#define TSU_FZ " + std::to_string(fz) + "\n";
+  int minb = 4;
+  if (const char* e = getenv("TSU_JIT_MINB")) minb = atoi(e) > 0 ? atoi(e) : 4;
+  src += "#define TSU_JIT_MINB " + std::to_string(minb) + "\n";
+  if (getenv("TSU_JIT_WIDE")) src += "#define TSU_JIT_WIDE 1\n";
   src +=
       "#include \"ising2d_fast.cuh\"\n"
-      "extern \"C\" __global__ void __launch_bounds__(128, 4) tsu_jit_half_sweep(tsu_fast::SweepParams P) {\n"
+      "extern \"C\" __global__ void __launch_bounds__(128, TSU_JIT_MINB) tsu_jit_half_sweep(tsu_fast::SweepParams P) {\n"
       "  tsu_fast::half_sweep_fast_body(P);\n}\n";
   void* prog = nullptr;
   if (g_jit.nvrtcCreateProgram(&prog, src.c_str(), "tsu_jit.cu", 0, nullptr, nullptr) != 0) return 0;

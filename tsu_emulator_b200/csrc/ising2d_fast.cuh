@@ -285,14 +285,30 @@ __device__ __forceinline__ void half_sweep_fast_body(const SweepParams& P) {
       // plane first; planes 4-7 (second Philox call) are consumed before planes 0-3 are generated
 #pragma unroll
       for (int k = 0; k < 4; ++k) eq[k] = 0xffffffffu;
+#ifdef TSU_JIT_WIDE
+      // all eight Philox calls of the row are issued before any plane is consumed (more independent chains)
+      uint32_t rw[2][4][4];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          q.c0_base = (uint32_t)(w0 + k) | colour_bits;
+          const tsu_u32x4 pp = lattice_call(q, hh ? TSU_KIND_PLANE1 : TSU_KIND_PLANE0);
+          rw[hh][k][0] = pp.x; rw[hh][k][1] = pp.y; rw[hh][k][2] = pp.z; rw[hh][k][3] = pp.w;
+        }
+#endif
 #pragma unroll
       for (int half = 1; half >= 0; --half) {
         uint32_t r[4][4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
+#ifdef TSU_JIT_WIDE
+          r[k][0] = rw[half][k][0]; r[k][1] = rw[half][k][1]; r[k][2] = rw[half][k][2]; r[k][3] = rw[half][k][3];
+#else
           q.c0_base = (uint32_t)(w0 + k) | colour_bits;
           const tsu_u32x4 pp = lattice_call(q, half ? TSU_KIND_PLANE1 : TSU_KIND_PLANE0);
           r[k][0] = pp.x; r[k][1] = pp.y; r[k][2] = pp.z; r[k][3] = pp.w;
+#endif
         }
 #pragma unroll
         for (int kk = 3; kk >= 0; --kk) {
