@@ -333,7 +333,9 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
           }
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           cp_async_wait<kLook>();  // this thread's pieces of the J tile of this chunk have landed
-          fence_async_smem();      // cp.async writes -> visible to the tensor core (async proxy)
+          // NOTE: no fence.proxy.async here.  It lowers to MEMBAR.ALL.CTA, which waits for ALL of the thread's
+          // outstanding memory operations - including the J-tile cp.asyncs just issued for kLook chunks ahead -
+          // i.e. one full L2/HBM latency per chunk.  The MMA warp issues the proxy fence after its acquire.
           tc_fence_before();
           mbar_arrive(&sm.full[sa]);
         }
@@ -361,6 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
         for (int cc = 0; cc < n_chunks; ++cc) {
           mbar_wait(&sm.full[sa], (full_phase >> sa) & 1u);
           full_phase ^= 1u << sa;
+          fence_async_smem();  // producers' cp.async (generic proxy) writes, acquired above -> async proxy reads
           tc_fence_after();
           if (elect_one()) {
             const uint64_t bd0 = b_desc0 + (uint64_t)((uint32_t)sb * kStageUnits);
