@@ -352,7 +352,8 @@ def run_b200_arm(args):
             "frac": achieved / peak,
             "traffic": profiled_traffic(),
             "peak_source": peak_src,
-            "kernel": "half_sweep_fast_kernel",
+            "kernel": ("tsu_jit_half_sweep (NVRTC specialisation of half_sweep_fast_body for this temperature)"
+                       if getattr(eng, "_jit", 0) > 0 else "half_sweep_fast_kernel"),
             "algorithmic_bytes_per_launch": alg_bytes_per_launch,
             "launch_ms": launch_s * 1e3,
         },

@@ -160,6 +160,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+#ifdef TSU_TC_TIMING  // per-role stall accounting, see tools/tc_timing.py
+__device__ unsigned long long g_tc_timing[16];
+#define TC_T0() const long long t0__ = clock64()
+#define TC_ACC(i) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) atomicAdd(&g_tc_timing[i], (unsigned long long)(clock64() - t0__)); } while (0)
+#else
+#define TC_T0() do {} while (0)
+#define TC_ACC(i) do {} while (0)
+#endif
+
 struct TcParams {
   const __nv_bfloat16* J;   // [N][N] row-major coupling matrix (row i = couplings INTO site i)
   const float* bias;        // [N] or nullptr
@@ -282,8 +291,10 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
         int lkc = ld_cc + (ld_blk >> 2) + 1;
         if (lkc >= n_chunks) lkc -= n_chunks;
         if (ld_count >= kBStages) {
+          TC_T0();
           mbar_wait(&sm.b_empty[ld_stage], (b_phase >> ld_stage) & 1u);
           b_phase ^= 1u << ld_stage;
+          if (warp == 0) TC_ACC(3);
         }
 #pragma unroll
         for (int p = 0; p < kBlk * (kKC / 8) / kChains; ++p) {
@@ -310,14 +321,21 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
           if (kc >= n_chunks) kc -= n_chunks;
           load_b();
           const int need = (cc >= n_chunks - 2) ? gb : gb - 1;
-          while (ready_seen < need) {
-            mbar_wait(&sm.state_ready[ready_seen & 3], (uint32_t)((ready_seen >> 2) & 1));
-            ++ready_seen;
+          {
+            TC_T0();
+            while (ready_seen < need) {
+              mbar_wait(&sm.state_ready[ready_seen & 3], (uint32_t)((ready_seen >> 2) & 1));
+              ++ready_seen;
+            }
+            if (warp == 0) TC_ACC(4);
           }
           if (g >= kAStages) {
+            TC_T0();
             mbar_wait(&sm.a_empty[sa], (a_phase >> sa) & 1u);
             a_phase ^= 1u << sa;
+            if (warp == 0) TC_ACC(5);
           }
+          TC_T0();
           // 128 bits of this chain -> 64 packed bf16 pairs -> 64 TMEM columns of the chain's lane
           const uint32_t a_col = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kAccCols + sa * (kKC / 2));
 #pragma unroll
@@ -338,6 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
           // i.e. one full L2/HBM latency per chunk.  The MMA warp issues the proxy fence after its acquire.
           tc_fence_before();
           mbar_arrive(&sm.full[sa]);
+          if (warp == 0) TC_ACC(6);
         }
         if (++sa == kAStages) sa = 0;
       }
@@ -357,12 +376,19 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
       for (int gb = 0; gb < total_blocks; ++gb) {
         const int buf = gb & 1;
         if (gb >= 2) {  // the epilogue has read this accumulator buffer out
+          TC_T0();
           mbar_wait(&sm.acc_free[buf], (free_phase >> buf) & 1u);
           free_phase ^= 1u << buf;
+          TC_ACC(2);
         }
         for (int cc = 0; cc < n_chunks; ++cc) {
-          mbar_wait(&sm.full[sa], (full_phase >> sa) & 1u);
+          {
+            TC_T0();
+            mbar_wait(&sm.full[sa], (full_phase >> sa) & 1u);
+            TC_ACC(0);
+          }
           full_phase ^= 1u << sa;
+          TC_T0();
           fence_async_smem();  // producers' cp.async (generic proxy) writes, acquired above -> async proxy reads
           tc_fence_after();
           if (elect_one()) {
@@ -380,6 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
             if (cc == n_chunks - 1) umma_commit(&sm.acc_full[buf]);
           }
           __syncwarp();
+          TC_ACC(1);
           if (++sa == kAStages) sa = 0;
           if (++sb == kBStages) sb = 0;
         }
@@ -418,8 +445,13 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
       }
       if (gb + 1 < total_blocks) jd = load_diag((gb + 1) % n_blocks);
       named_bar_sync(1, kChains);
-      mbar_wait_backoff(&sm.acc_full[buf], (accf_phase >> buf) & 1u);
+      {
+        TC_T0();
+        mbar_wait_backoff(&sm.acc_full[buf], (accf_phase >> buf) & 1u);
+        if (warp == 8) TC_ACC(8);
+      }
       accf_phase ^= 1u << buf;
+      TC_T0();
       tc_fence_after();
       float h[kBlk];
       tmem_ld32(tmem_lane + (uint32_t)(buf * kPartials * kBlk), h);
@@ -468,6 +500,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
         sm.sbits[blk][row] = w;
       }
       mbar_arrive(&sm.state_ready[gb & 3]);  // release: the producers may expand chunks holding this block
+      if (warp == 8) TC_ACC(9);
     }
     if (!P.gemm_only && chain_ok) {  // unpack the final bits of this chain
       for (int w = 0; w < N / 32; ++w) {
@@ -522,6 +555,16 @@ extern "C" int tsu_dense_gibbs_tc_run(const void* d_J_bf16, const float* d_bias,
   P.gemm_only = 0;
   return launch_tc(P, tsu_stream(stream));
 }
+
+#ifdef TSU_TC_TIMING
+extern "C" int tsu_dense_tc_debug_timing(unsigned long long* h_out16, int reset) {
+  if (reset) {
+    unsigned long long z[16] = {0};
+    return (int)cudaMemcpyToSymbol(g_tc_timing, z, sizeof z);
+  }
+  return (int)cudaMemcpyFromSymbol(h_out16, g_tc_timing, sizeof(unsigned long long) * 16);
+}
+#endif
 
 extern "C" int tsu_dense_tc_debug_fields(const void* d_J_bf16, const uint8_t* d_state, int n_chains, int N,
                                          float* d_fields, uintptr_t stream) {
