@@ -18,6 +18,7 @@
 // operand A never touches shared memory, so no generic->async proxy fence and no smem bandwidth is spent
 // on it.  The matching J tile (operand B, K-major, no swizzle) is streamed from L2 with cp.async.
 
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -179,6 +180,7 @@ struct TcParams {
   float T;
   uint32_t k0, k1, sweep0, chain0;
   int gemm_only;            // diagnostics: no spin update (fields of the initial state for every site)
+  int dbg;                  // diagnostics (TSU_TC_DEBUG, timing experiments only): 1 no MMA, 2 no A expansion, 4 no J loads
 };
 
 constexpr int kGroups = 2;        // producer groups: group q expands the K-chunks with (chunk index % kGroups) == q,
@@ -290,14 +292,14 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
       if (ld_sweep < P.n_sweeps) {
         int lkc = ld_cc + (ld_blk >> 2) + 1;
         if (lkc >= n_chunks) lkc -= n_chunks;
-        if (ld_count >= kBStages) {
+        if (ld_count >= kBStages && !(P.dbg & 16)) {
           TC_T0();
           mbar_wait(&sm.b_empty[ld_stage], (b_phase >> ld_stage) & 1u);
           b_phase ^= 1u << ld_stage;
           if (warp == 0) TC_ACC(3);
         }
 #pragma unroll
-        for (int p = 0; p < kBlk * (kKC / 8) / kChains; ++p) {
+        for (int p = 0; p < kBlk * (kKC / 8) / kChains && !(P.dbg & 4); ++p) {
           const int piece = row + kChains * p;
           const int n = piece / (kKC / 8), k16 = piece % (kKC / 8);
           cp_async16(&sm.b[ld_stage][k16][n >> 3][n & 7][0], P.J + (size_t)(ld_blk * kBlk + n) * N + lkc * kKC + 8 * k16);
@@ -339,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
           // 128 bits of this chain -> 64 packed bf16 pairs -> 64 TMEM columns of the chain's lane
           const uint32_t a_col = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kAccCols + sa * (kKC / 2));
 #pragma unroll
-          for (int q = 0; q < kKC / 32; ++q) {
+          for (int q = 0; q < kKC / 32 && !(P.dbg & 2); ++q) {
             const uint32_t w = sm.sbits[(kKC / 32) * kc + q][row];
             uint32_t r[16];
 #pragma unroll
@@ -349,8 +351,8 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
             }
             tmem_st16(a_col + 16 * q, r);
           }
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          cp_async_wait<kLook>();  // this thread's pieces of the J tile of this chunk have landed
+          if (!(P.dbg & 32)) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          if (!(P.dbg & 64)) cp_async_wait<kLook>();  // this thread's pieces of the J tile of this chunk have landed
           // NOTE: no fence.proxy.async here.  It lowers to MEMBAR.ALL.CTA, which waits for ALL of the thread's
           // outstanding memory operations - including the J-tile cp.asyncs just issued for kLook chunks ahead -
           // i.e. one full L2/HBM latency per chunk.  The MMA warp issues the proxy fence after its acquire.
@@ -389,20 +391,20 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
           }
           full_phase ^= 1u << sa;
           TC_T0();
-          fence_async_smem();  // producers' cp.async (generic proxy) writes, acquired above -> async proxy reads
+          if (!(P.dbg & 8)) fence_async_smem();  // producers' cp.async (generic proxy) writes, acquired above -> async proxy reads
           tc_fence_after();
           if (elect_one()) {
             const uint64_t bd0 = b_desc0 + (uint64_t)((uint32_t)sb * kStageUnits);
             const uint32_t a0 = tmem_d + (uint32_t)(kAccCols + sa * (kKC / 2));
             const uint32_t d0 = tmem_d + (uint32_t)(buf * kPartials * kBlk);
 #pragma unroll
-            for (int j = 0; j < kKC / 16; ++j) {
+            for (int j = 0; j < kKC / 16 && !(P.dbg & 1); ++j) {
               // K-steps rotate over kPartials accumulators; the epilogue adds them up
               umma_bf16_ts(d0 + (uint32_t)((j % kPartials) * kBlk), a0 + 8u * j, bd0 + (uint64_t)(j * kStepUnits), idesc,
                            (cc > 0 || j >= kPartials) ? 1u : 0u);
             }
             umma_commit(&sm.a_empty[sa]);
-            umma_commit(&sm.b_empty[sb]);
+            if (!(P.dbg & 16)) umma_commit(&sm.b_empty[sb]);
             if (cc == n_chunks - 1) umma_commit(&sm.acc_full[buf]);
           }
           __syncwarp();
@@ -419,7 +421,6 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
     const bool chain_ok = chain < P.n_chains;
     const uint32_t tmem_lane = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
     const float T = P.T_chain ? (float)P.T_chain[chain_ok ? chain : 0] : P.T;
-    const float invT = 1.0f / T;
     const uint32_t chain_g = P.chain0 + (uint32_t)chain;
     uint32_t accf_phase = 0;
     // diagonal block J[blk, blk]: 8 bf16 per thread (row i0 + row/4, columns i0 + 8 (row%4) ..), fetched one
@@ -445,6 +446,26 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
       }
       if (gb + 1 < total_blocks) jd = load_diag((gb + 1) % n_blocks);
       named_bar_sync(1, kChains);
+      // Acceptance thresholds of the block, computed while the tensor core is still accumulating:
+      //   u < sigmoid(h / T)  <=>  h > T * logit(u)          (gibbs.py:61-77,126; strict <)
+      // and the clamp of gibbs.py:65-70 (|h/T| > 20 -> p = 1 / 0) is the clamp of the threshold to +-20 T.
+      // This takes exp, the division and the Philox call off the site-to-site dependency chain: per site the
+      // chain is compare -> select -> fma.
+      float thr[kBlk];
+      if (!P.gemm_only) {
+#pragma unroll
+        for (int i = 0; i < kBlk; i += 4) {
+          const tsu_u32x4 o = tsu_philox4x32_10((uint32_t)((i0 + i) >> 2), chain_g, P.sweep0 + (uint32_t)sweep,
+                                                TSU_STREAM_DENSE_TC, P.k0, P.k1);
+          const uint32_t r4[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float u = (float)(r4[k] >> 8) * (1.0f / 16777216.0f);  // 24-bit uniform, exact in fp32
+            const float lg = (__log2f(u) - __log2f(1.0f - u)) * 0.69314718056f;
+            thr[i + k] = fminf(fmaxf(lg, -20.0f), 20.0f) * T;
+          }
+        }
+      }
       {
         TC_T0();
         mbar_wait_backoff(&sm.acc_full[buf], (accf_phase >> buf) & 1u);
@@ -476,28 +497,21 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
       } else {
         // sequential heat-bath update of the 32 sites of this block for this thread's chain (gibbs.py:153-160)
         static_assert(kBlk == 32, "one state word per block");
-        uint32_t w = sm.sbits[blk][row];
-        tsu_u32x4 o = {0u, 0u, 0u, 0u};
+        const uint32_t w_old = sm.sbits[blk][row];
+        uint32_t w_new = 0;
 #pragma unroll
         for (int i = 0; i < kBlk; ++i) {
-          if ((i & 3) == 0)  // one Philox block serves 4 consecutive sites of a chain
-            o = tsu_philox4x32_10((uint32_t)((i0 + i) >> 2), chain_g, P.sweep0 + (uint32_t)sweep, TSU_STREAM_DENSE_TC,
-                                  P.k0, P.k1);
-          const uint32_t r32 = (i & 3) == 0 ? o.x : ((i & 3) == 1 ? o.y : ((i & 3) == 2 ? o.z : o.w));
-          const float u = (float)(r32 >> 8) * (1.0f / 16777216.0f);  // 24-bit uniform, exact in fp32
           if (P.fields_out && chain_ok) P.fields_out[(size_t)chain * N + i0 + i] = h[i];  // field at visit time
-          const float x = h[i] * invT;
-          float pacc = 1.0f / (1.0f + __expf(-x));                    // gibbs.py:61-77 incl. the clamp
-          pacc = x > 20.0f ? 1.0f : (x < -20.0f ? 0.0f : pacc);
-          const uint32_t nb = u < pacc ? 1u : 0u;                     // gibbs.py:126 (strict <)
-          const uint32_t ob = (w >> i) & 1u;
-          const float delta = (float)nb - (float)ob;
-          w = (w & ~(1u << i)) | (nb << i);
+          const float d_up = ((w_old >> i) & 1u) ? 0.0f : 1.0f;   // new - old if the site comes out 1 ...
+          const float d_dn = d_up - 1.0f;                          // ... or 0 (both known before the chain)
+          const bool up = h[i] > thr[i];
+          const float delta = up ? d_up : d_dn;
+          w_new |= up ? (1u << i) : 0u;
           // not yet visited sites of the block see the new value (rank-1 correction, branch free)
 #pragma unroll
           for (int ip = i + 1; ip < kBlk; ++ip) h[ip] = fmaf(sm.jblk[i][ip], delta, h[ip]);
         }
-        sm.sbits[blk][row] = w;
+        sm.sbits[blk][row] = w_new;
       }
       mbar_arrive(&sm.state_ready[gb & 3]);  // release: the producers may expand chunks holding this block
       if (warp == 8) TC_ACC(9);
@@ -578,5 +592,6 @@ extern "C" int tsu_dense_tc_debug_fields(const void* d_J_bf16, const uint8_t* d_
   P.n_sweeps = 1;
   P.T = 1.0f;
   P.gemm_only = 1;
+  if (const char* e = getenv("TSU_TC_DEBUG")) P.dbg = atoi(e);
   return launch_tc(P, tsu_stream(stream));
 }
