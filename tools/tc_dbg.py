@@ -6,10 +6,9 @@ from tsu_emulator_b200 import _lib
 N, C = 4096, 2048
 J = (torch.randn(N, N, device="cuda") / N**0.5).to(torch.bfloat16)
 st = (torch.rand(C, N, device="cuda") < 0.5).to(torch.uint8)
-H = torch.empty((C, N), device="cuda")
-for it in range(3):
+for it in range(2):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); _lib.call("tsu_dense_tc_debug_fields", _lib.ptr(J), _lib.ptr(st), C, N, _lib.ptr(H), _lib.current_stream()); b.record()
+    a.record(); _lib.call("tsu_dense_gibbs_tc_run", _lib.ptr(J), None, _lib.ptr(st), C, N, 1.0, None, 4, 3, 0, 0, None, _lib.current_stream()); b.record()
     torch.cuda.synchronize()
-ms = a.elapsed_time(b)
-print(f"TSU_TC_DEBUG={os.environ.get('TSU_TC_DEBUG','0')}: gemm pass {ms:.3f} ms = {ms*1e-3*1.965e9/4096:.0f} clk/chunk")
+ms = a.elapsed_time(b) / 4
+print(f"TSU_TC_DEBUG={os.environ.get('TSU_TC_DEBUG','0')}: sweep {ms:.3f} ms = {ms*1e-3*1.965e9/4096:.0f} clk/chunk = {ms*1e-3*1.965e9/128:.0f} clk/block")

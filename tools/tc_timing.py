@@ -13,9 +13,11 @@ torch.cuda.synchronize(); f(None, 1)
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record(); _lib.call("tsu_dense_gibbs_tc_run", _lib.ptr(J), None, _lib.ptr(st), C, N, 1.0, None, 2, 3, 1, 0, None, _lib.current_stream()); b.record()
 torch.cuda.synchronize()
-out = (ctypes.c_ulonglong * 16)(); f(out, 0)
+out = (ctypes.c_ulonglong * 32)(); f(out, 0)
 ms = a.elapsed_time(b); total_clk = ms * 1e-3 * 1.965e9
-names = ["MMA wait full", "MMA fence+issue", "MMA wait acc_free", "P0 wait b_empty", "P0 wait state_ready", "P0 wait a_empty", "P0 expand+st+arrive", "-", "EPI wait acc_full", "EPI ld+update"]
+names = ["issuer0 wait full", "issuer1 wait full", "issuers wait acc_free", "P0 wait empty", "P0 wait state_ready", "P0 load+expand+arrive",
+         "-", "P1 wait empty", "P1 wait state_ready", "P1 load+expand+arrive", "-", "EPI wait acc_full", "EPI ld+update", "-", "-", "-",
+         "P0w0 load_b issue", "P0w0 lds+alu+sttm issue", "P0w0 wait::st", "P0w0 cp.async.wait", "P0w0 fence+syncwarp+arrive", "issuer0 membar+fence", "issuer0 mma+commit+syncwarp"]
 nchunks = 2 * 128 * 32
 print(f"2 sweeps: {ms:.2f} ms = {total_clk:.3e} clk; chunks per CTA = {nchunks}; {total_clk/nchunks:.0f} clk/chunk")
 for i, n in enumerate(names):

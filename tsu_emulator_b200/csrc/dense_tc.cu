@@ -13,10 +13,16 @@
 // sites of the block, which makes the result identical to a site-by-site sweep with the same fields.
 //
 // One CTA owns 128 chains (TMEM lane = chain).  The chain states stay resident in shared memory as bits
-// for the whole sweep (64 KB).  Each K-chunk of 128 sites is expanded to bf16 0/1 by the thread that owns
-// the chain and written straight into TENSOR MEMORY (tcgen05.st, lane = chain, column = K pair): the spin
-// operand A never touches shared memory, so no generic->async proxy fence and no smem bandwidth is spent
-// on it.  The matching J tile (operand B, K-major, no swizzle) is streamed from L2 with cp.async.
+// for the whole sweep (64 KB).  Each K-chunk of 128 sites is expanded to bf16 by the thread that owns the
+// chain and written straight into TENSOR MEMORY (tcgen05.st, lane = chain, column = K pair): the spin
+// operand A never touches shared memory.  A spin is encoded as 0.0 / 2.0: bf16 2.0 = 0x4000 has ONE set bit,
+// so a packed pair of spins is (word << s) & 0x40004000 - two integer instructions per register - and the
+// accumulated field is halved (exactly) in the epilogue.  The matching J tile (operand B, K-major, no
+// swizzle) is streamed from L2 with cp.async.
+//
+// The K-chunks of a block alternate between two independent pipelines (producer group of 4 warps + one MMA
+// issuer warp + own operand rings + own accumulator), so that the per-chunk synchronisation latencies
+// (mbarrier wake-ups, TMEM store drain, commit) of one pipeline hide behind the other.
 
 #include <cstdlib>
 #include <cuda_bf16.h>
@@ -29,12 +35,14 @@ namespace {
 constexpr int kChains = 128;  // chains per CTA = UMMA M = TMEM lanes
 constexpr int kBlk = 32;      // sites per block = UMMA N
 constexpr int kKC = 128;      // K-chunk (sites) per pipeline stage
-constexpr int kAStages = 4;   // expanded spin tiles in tensor memory (64 columns each)
-constexpr int kPartials = 4;  // independent partial accumulators: consecutive MMAs never wait on each other's result
-constexpr int kAccCols = 2 * kPartials * kBlk;  // two buffers x 4 partial 32-column fp32 accumulators = 256 columns
-// tensor memory: 256 accumulator + 4 x 64 operand columns = 512 columns
-constexpr int kBStages = 14;  // J tile ring (8 KB each); every producer group owns kBStages / kGroups slots
-constexpr int kLook = 5;      // a group requests J tiles 5 of its own chunks ahead (must be < slots per group)
+constexpr int kPipes = 2;     // independent producer/issuer pipelines; chunk cc of a block goes to pipeline cc % kPipes
+constexpr int kASlots = 3;    // per pipeline: expanded spin tiles in tensor memory (64 columns each)
+constexpr int kLook = 4;      // per pipeline: J tiles are requested 4 of its own chunks ahead
+constexpr int kBSlots = kLook + kASlots;  // per pipeline: J tile ring (8 KB each).  With this depth the J slot of chunk
+                                          // m + kLook is the one chunk m - kASlots used: ONE "empty" barrier frees both
+constexpr int kAccCols = 2 * kPipes * kBlk;  // two buffers x one 32-column fp32 accumulator per pipeline = 128 columns
+constexpr int kACols = kKC / 2;              // 32-bit columns of one expanded spin tile
+static_assert(kAccCols + kPipes * kASlots * kACols <= 512, "tensor memory budget");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -162,10 +170,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 }
 
 #ifdef TSU_TC_TIMING  // per-role stall accounting, see tools/tc_timing.py
-__device__ unsigned long long g_tc_timing[16];
-#define TC_T0() const long long t0__ = clock64()
+__device__ unsigned long long g_tc_timing[32];
+#define TC_T0() long long t0__ = clock64()
 #define TC_ACC(i) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) atomicAdd(&g_tc_timing[i], (unsigned long long)(clock64() - t0__)); } while (0)
+#define TC_NEXT(i) do { const long long t1__ = clock64(); if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) atomicAdd(&g_tc_timing[i], (unsigned long long)(t1__ - t0__)); t0__ = t1__; } while (0)
 #else
+#define TC_NEXT(i) do {} while (0)
 #define TC_T0() do {} while (0)
 #define TC_ACC(i) do {} while (0)
 #endif
@@ -183,29 +193,35 @@ struct TcParams {
   int dbg;                  // diagnostics (TSU_TC_DEBUG, timing experiments only): 1 no MMA, 2 no A expansion, 4 no J loads
 };
 
-constexpr int kGroups = 2;        // producer groups: group q expands the K-chunks with (chunk index % kGroups) == q,
-                                 // so the per-chunk latencies (TMEM store, fences, barrier wake-ups) of the groups overlap
-constexpr int kProducers = 128 * kGroups;  // warps 0-7: 4 warps (128 chains) per group
-constexpr int kThreads = 416;    // + warps 8-11 epilogue (thread = chain = TMEM lane) + warp 12 MMA issuer
+constexpr int kProducers = 128 * kPipes;            // warps 0-7: 4 warps (128 chains) per pipeline
+constexpr int kEpilogue0 = kProducers / 32;         // warps 8-11: epilogue (thread = chain = TMEM lane)
+constexpr int kIssuer0 = kEpilogue0 + 4;            // warps 12-13: MMA issuers
+constexpr int kThreads = 32 * (kIssuer0 + kPipes);  // 448
 
-// shared memory carve-up (~120 KB)
+// position of site i (0-31 of a block) inside a state word: even sites in the low half, odd sites in the high
+// half, so that (word >> j) & 0x00010001 is the pair (2j, 2j+1)
+__host__ __device__ constexpr int site_bit(int i) { return (i >> 1) + 16 * (i & 1); }
+
+// shared memory carve-up (~182 KB)
 struct TcSmem {
-  uint32_t sbits[4096 / 32][kChains];                                     // chain states, word-major: sbits[w][chain]
-  __align__(128) __nv_bfloat16 b[kBStages][kKC / 8][kBlk / 8][8][8];
+  uint32_t sbits[4096 / 32][kChains];        // chain states, word-major: sbits[w][chain], bit order = site_bit()
+  __align__(128) __nv_bfloat16 b[kPipes][kBSlots][kKC / 8][kBlk / 8][8][8];
   __align__(16) float jblk[kBlk][kBlk + 4];  // J[blk, blk] as fp32, transposed: jblk[i][i'] = J[i0+i'][i0+i]
-  __align__(128) uint4 lut[256][8];          // byte -> 8 bf16 (0.0 / 1.0), one copy per lane%8: a quarter-warp LDS.128
-                                             // touches 8 different 16-byte bank groups whatever the bytes are
-  __align__(8) uint64_t full[kAStages];      // producers -> MMA: A stage written, J tile landed      (count 128)
-  __align__(8) uint64_t a_empty[kAStages];   // MMA -> producers: the MMAs that read the A stage are done (commit)
-  __align__(8) uint64_t b_empty[kBStages];   // MMA -> producers: J ring slot free                       (commit)
-  __align__(8) uint64_t acc_full[2];         // MMA -> epilogue: accumulator buffer complete             (commit)
-  __align__(8) uint64_t acc_free[2];         // epilogue -> MMA: accumulator buffer read out             (count 128)
-  __align__(8) uint64_t state_ready[4];      // epilogue -> producers: bits of block gb written (ring, count 128)
+  __align__(8) uint64_t full[kPipes][kASlots];   // producers -> issuer: A slot written, J tile landed  (one arrival per warp)
+  __align__(8) uint64_t empty[kPipes][kASlots];  // issuer -> producers: the MMAs reading the A slot (and its J slot) are done (commit)
+  __align__(8) uint64_t acc_full[2];         // issuers -> epilogue: accumulator buffer complete          (one commit per pipeline)
+  __align__(8) uint64_t acc_free[2];         // epilogue -> issuers: accumulator buffer read out          (one arrival per warp)
+  __align__(8) uint64_t state_ready[4];      // epilogue -> producers: bits of block gb written (ring, one arrival per warp)
   uint32_t tmem_base;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// all lanes have done their part: one lane arrives for the warp (__syncwarp orders the lanes' writes before it)
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
@@ -218,17 +234,10 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
   const int N = P.N;
   const int n_blocks = N / kBlk, n_chunks = N / kKC;
   const int total_blocks = n_blocks * P.n_sweeps;
+  const int n_active = n_chunks < kPipes ? n_chunks : kPipes;  // pipelines that ever get a chunk
   static_assert(kKC == 4 * kBlk, "a K-chunk holds four blocks");
 
   // ---- one-time setup -------------------------------------------------------------------------
-  for (int i = tid; i < 256 * 8; i += kThreads) {
-    const int byte = i >> 3;
-    uint32_t w[4];
-#pragma unroll
-    for (int p = 0; p < 4; ++p)
-      w[p] = ((byte >> (2 * p)) & 1 ? 0x3F80u : 0u) | ((byte >> (2 * p + 1)) & 1 ? 0x3F800000u : 0u);
-    sm.lut[byte][i & 7] = make_uint4(w[0], w[1], w[2], w[3]);
-  }
   if (tid < kChains) {  // pack this chain's bits
     const int chain = blockIdx.x * kChains + tid;
     for (int w = 0; w < N / 32; ++w) {
@@ -237,27 +246,28 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
         const uint8_t* src = P.state + (size_t)chain * N + 32 * w;
 #pragma unroll
         for (int b = 0; b < 32; b += 4) {
-          const uint32_t v = *reinterpret_cast<const uint32_t*>(src + b);
-          x |= ((v & 1u) | ((v >> 7) & 2u) | ((v >> 14) & 4u) | ((v >> 21) & 8u)) << b;
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(src + b);  // sites b .. b+3
+          x |= ((v & 1u) | ((v >> 15) & 2u)) << (b >> 1);                  // even sites b, b+2
+          x |= (((v >> 8) & 1u) | ((v >> 23) & 2u)) << (16 + (b >> 1));    // odd sites b+1, b+3
         }
       }
       sm.sbits[w][tid] = x;
     }
   }
   if (tid == 0) {
-    for (int s = 0; s < kAStages; ++s) {
-      mbar_init(&sm.full[s], kChains);
-      mbar_init(&sm.a_empty[s], 1);
-    }
-    for (int s = 0; s < kBStages; ++s) mbar_init(&sm.b_empty[s], 1);
+    for (int q = 0; q < kPipes; ++q)
+      for (int s = 0; s < kASlots; ++s) {
+        mbar_init(&sm.full[q][s], 4);
+        mbar_init(&sm.empty[q][s], 1);
+      }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&sm.acc_full[s], 1);
-      mbar_init(&sm.acc_free[s], kChains);
+      mbar_init(&sm.acc_full[s], n_active);
+      mbar_init(&sm.acc_free[s], 4);
     }
-    for (int s = 0; s < 4; ++s) mbar_init(&sm.state_ready[s], kChains);
+    for (int s = 0; s < 4; ++s) mbar_init(&sm.state_ready[s], 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 12) {
+  if (warp == kIssuer0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm.tmem_base)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -266,113 +276,110 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
   tc_fence_after();
   const uint32_t tmem_d = sm.tmem_base;
 
-  if (warp < 8) {
+  if (warp < kEpilogue0) {
     // ===================== producers: expand spins to bf16 A tiles, stream J tiles ======================
-    // group = warp / 4 handles every kGroups-th chunk; inside a group, thread = chain (TMEM lane)
-    const int group = warp >> 2, row = tid & (kChains - 1);
-    uint32_t a_phase = 0, b_phase = 0;
-    int ready_seen = 0;  // number of state_ready phases consumed (block gb needs gb of them for its last two chunks)
-    // J tile requests run kLook of the group's own chunks ahead (across blocks and sweeps)
-    int ld_sweep = 0, ld_blk = 0, ld_cc = 0, ld_stage = 0;
-    long long ld_count = 0;
-    auto ld_advance = [&](int n) {  // skip n chunks of the global sequence
-      for (int i = 0; i < n; ++i) {
-        ++ld_count;
-        if (++ld_stage == kBStages) ld_stage = 0;
-        if (++ld_cc == n_chunks) {
-          ld_cc = 0;
-          if (++ld_blk == n_blocks) {
-            ld_blk = 0;
-            ++ld_sweep;
+    // pipeline q = warp / 4 handles the chunks cc = q, q + kPipes, ... of every block; thread = chain (TMEM lane)
+    const int q = warp >> 2, row = tid & (kChains - 1);
+    if (q < n_active) {
+      // J tile requests run kLook of the pipeline's own chunks ahead (across blocks and sweeps)
+      int ld_gb = 0, ld_blk = 0, ld_cc = q, ld_slot = 0;
+      auto load_b = [&]() {
+        if (ld_gb < total_blocks) {
+          int lkc = ld_cc + (ld_blk >> 2) + 1;
+          if (lkc >= n_chunks) lkc -= n_chunks;
+          const __nv_bfloat16* src = P.J + (size_t)(ld_blk * kBlk) * N + lkc * kKC;
+          // 16-byte pieces: a warp instruction covers 16 rows x one 32-byte sector (full sectors from L2) and lands
+          // in two 256-byte runs of the tile (4 shared-memory wavefronts, the minimum for 512 bytes)
+          if (!(P.dbg & 4)) {
+#pragma unroll
+            for (int p = 0; p < kBlk * (kKC / 8) / kChains; ++p) {
+              const int n = ((row & 31) >> 1) + 16 * (p & 1), k16 = 2 * ((row >> 5) + 4 * (p >> 1)) + (row & 1);
+              cp_async16(&sm.b[q][ld_slot][k16][n >> 3][n & 7][0], src + (size_t)n * N + 8 * k16);
+            }
+          }
+          if (++ld_slot == kBSlots) ld_slot = 0;
+          ld_cc += kPipes;
+          if (ld_cc >= n_chunks) {
+            ld_cc = q;
+            ++ld_gb;
+            if (++ld_blk == n_blocks) ld_blk = 0;
           }
         }
-      }
-    };
-    auto load_b = [&]() {
-      if (ld_sweep < P.n_sweeps) {
-        int lkc = ld_cc + (ld_blk >> 2) + 1;
-        if (lkc >= n_chunks) lkc -= n_chunks;
-        if (ld_count >= kBStages && !(P.dbg & 16)) {
-          TC_T0();
-          mbar_wait(&sm.b_empty[ld_stage], (b_phase >> ld_stage) & 1u);
-          b_phase ^= 1u << ld_stage;
-          if (warp == 0) TC_ACC(3);
-        }
-#pragma unroll
-        for (int p = 0; p < kBlk * (kKC / 8) / kChains && !(P.dbg & 4); ++p) {
-          const int piece = row + kChains * p;
-          const int n = piece / (kKC / 8), k16 = piece % (kKC / 8);
-          cp_async16(&sm.b[ld_stage][k16][n >> 3][n & 7][0], P.J + (size_t)(ld_blk * kBlk + n) * N + lkc * kKC + 8 * k16);
-        }
-        ld_advance(kGroups);
-      }
-      cp_async_commit();  // (an empty group at the tail keeps the group count uniform)
-    };
-    static_assert(kBStages % kGroups == 0 && kAStages % kGroups == 0 && kLook < kBStages / kGroups, "ring ownership");
-    ld_advance(group);                       // first chunk of this group
-    for (int i = 0; i < kLook; ++i) load_b();
-    long long g = 0;
-    int sa = 0;
-    for (int gb = 0; gb < total_blocks; ++gb) {
-      const int blk = gb % n_blocks;
-      for (int cc = 0; cc < n_chunks; ++cc, ++g) {
-        if ((int)(g % kGroups) == group) {
+        cp_async_commit();  // (an empty group at the tail keeps the group count uniform)
+      };
+      for (int i = 0; i < kLook; ++i) load_b();
+      uint32_t empty_phase = 0;
+      int ready_seen = 0;  // number of state_ready phases consumed (block gb needs gb of them for its last two chunks)
+      int sa = 0;
+      long long m = 0;     // own chunks done
+      for (int gb = 0; gb < total_blocks; ++gb) {
+        const int blk = gb % n_blocks;
+        for (int cc = q; cc < n_chunks; cc += kPipes, ++m) {
           // chunk order: own + 1, ..., own - 1, own.  The two last chunks may hold the previous block's sites,
           // so they wait for that block's update; everything earlier only needs older state.
           int kc = cc + (blk >> 2) + 1;
           if (kc >= n_chunks) kc -= n_chunks;
+          if (m >= kASlots) {  // the MMAs of own chunk m - kASlots are done: A slot sa and the J slot of chunk m + kLook are free
+            TC_T0();
+            mbar_wait(&sm.empty[q][sa], (empty_phase >> sa) & 1u);
+            empty_phase ^= 1u << sa;
+            if ((warp & 3) == 0) TC_ACC(3 + 4 * q);
+          }
+#ifdef TSU_TC_TIMING
+          long long tl0__ = clock64();
+#endif
           load_b();
+#ifdef TSU_TC_TIMING
+          if (warp == 0 && blockIdx.x == 0 && (tid & 31) == 0) atomicAdd(&g_tc_timing[16], (unsigned long long)(clock64() - tl0__));
+#endif
           const int need = (cc >= n_chunks - 2) ? gb : gb - 1;
-          {
+          if (ready_seen < need) {
             TC_T0();
             while (ready_seen < need) {
               mbar_wait(&sm.state_ready[ready_seen & 3], (uint32_t)((ready_seen >> 2) & 1));
               ++ready_seen;
             }
-            if (warp == 0) TC_ACC(4);
-          }
-          if (g >= kAStages) {
-            TC_T0();
-            mbar_wait(&sm.a_empty[sa], (a_phase >> sa) & 1u);
-            a_phase ^= 1u << sa;
-            if (warp == 0) TC_ACC(5);
+            if ((warp & 3) == 0) TC_ACC(4 + 4 * q);
           }
           TC_T0();
           // 128 bits of this chain -> 64 packed bf16 pairs -> 64 TMEM columns of the chain's lane
-          const uint32_t a_col = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kAccCols + sa * (kKC / 2));
+          const uint32_t a_col = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kAccCols + (q * kASlots + sa) * kACols);
 #pragma unroll
-          for (int q = 0; q < kKC / 32 && !(P.dbg & 2); ++q) {
-            const uint32_t w = sm.sbits[(kKC / 32) * kc + q][row];
+          for (int w4 = 0; w4 < kKC / 32 && !(P.dbg & 2); ++w4) {
+            const uint32_t w = sm.sbits[(kKC / 32) * kc + w4][row];
             uint32_t r[16];
 #pragma unroll
-            for (int by = 0; by < 4; ++by) {
-              const uint4 e = sm.lut[(w >> (8 * by)) & 0xFFu][tid & 7];
-              r[4 * by] = e.x; r[4 * by + 1] = e.y; r[4 * by + 2] = e.z; r[4 * by + 3] = e.w;
-            }
-            tmem_st16(a_col + 16 * q, r);
+            for (int j = 0; j < 15; ++j) r[j] = (w << (14 - j)) & 0x40004000u;  // sites 2j (low half), 2j+1 (high half)
+            r[15] = (w >> 1) & 0x40004000u;
+            tmem_st16(a_col + 16 * w4, r);
           }
-          if (!(P.dbg & 32)) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          if (!(P.dbg & 64)) cp_async_wait<kLook>();  // this thread's pieces of the J tile of this chunk have landed
+          if (warp == 0) TC_NEXT(17);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          if (warp == 0) TC_NEXT(18);
+          cp_async_wait<kLook>();  // this thread's pieces of the J tile of this chunk have landed
+          if (warp == 0) TC_NEXT(19);
           // NOTE: no fence.proxy.async here.  It lowers to MEMBAR.ALL.CTA, which waits for ALL of the thread's
           // outstanding memory operations - including the J-tile cp.asyncs just issued for kLook chunks ahead -
-          // i.e. one full L2/HBM latency per chunk.  The MMA warp issues the proxy fence after its acquire.
+          // i.e. one full L2/HBM latency per chunk.  The issuer warp executes the proxy fence after its acquire.
           tc_fence_before();
-          mbar_arrive(&sm.full[sa]);
-          if (warp == 0) TC_ACC(6);
+          warp_arrive(&sm.full[q][sa]);
+          if (warp == 0) TC_NEXT(20);
+          if (warp == 4) TC_ACC(9);
+          if (++sa == kASlots) sa = 0;
         }
-        if (++sa == kAStages) sa = 0;
       }
     }
-  } else if (warp == 12) {
-    // ===================== MMA issuer: one elected lane feeds the tensor core ===========================
+  } else if (warp >= kIssuer0) {
+    // ===================== MMA issuers: one elected lane per pipeline feeds the tensor core ================
     // The whole warp runs the loop (uniform control flow keeps counters and descriptors in uniform registers);
     // only the tcgen05.mma / commit instructions are issued by the elected lane.
-    {
+    const int q = warp - kIssuer0;
+    if (q < n_active) {
       const uint32_t idesc = umma_idesc(kChains, kBlk);
       constexpr uint32_t kLbo = (kBlk / 8) * 128, kSbo = 128;
-      const uint64_t b_desc0 = umma_desc(smem_u32(&sm.b[0][0][0][0][0]), kLbo, kSbo);
-      constexpr uint32_t kStageUnits = (uint32_t)(sizeof(sm.b[0]) >> 4);   // 16-byte units per ring slot
-      constexpr uint32_t kStepUnits = (2 * kLbo) >> 4;                      // per K = 16 step
+      const uint64_t b_desc0 = umma_desc(smem_u32(&sm.b[q][0][0][0][0][0]), kLbo, kSbo);
+      constexpr uint32_t kSlotUnits = (uint32_t)(sizeof(sm.b[0][0]) >> 4);  // 16-byte units per ring slot
+      constexpr uint32_t kStepUnits = (2 * kLbo) >> 4;                       // per K = 16 step
       uint32_t full_phase = 0, free_phase = 0;
       int sa = 0, sb = 0;
       for (int gb = 0; gb < total_blocks; ++gb) {
@@ -383,34 +390,31 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
           free_phase ^= 1u << buf;
           TC_ACC(2);
         }
-        for (int cc = 0; cc < n_chunks; ++cc) {
+        const uint32_t d0 = tmem_d + (uint32_t)((buf * kPipes + q) * kBlk);
+        for (int cc = q; cc < n_chunks; cc += kPipes) {
           {
             TC_T0();
-            mbar_wait(&sm.full[sa], (full_phase >> sa) & 1u);
-            TC_ACC(0);
+            mbar_wait(&sm.full[q][sa], (full_phase >> sa) & 1u);
+            TC_ACC(q);
           }
           full_phase ^= 1u << sa;
           TC_T0();
-          if (!(P.dbg & 8)) fence_async_smem();  // producers' cp.async (generic proxy) writes, acquired above -> async proxy reads
+          fence_async_smem();  // producers' cp.async (generic proxy) writes, acquired above -> async proxy reads
           tc_fence_after();
+          if (q == 0) TC_NEXT(21);
           if (elect_one()) {
-            const uint64_t bd0 = b_desc0 + (uint64_t)((uint32_t)sb * kStageUnits);
-            const uint32_t a0 = tmem_d + (uint32_t)(kAccCols + sa * (kKC / 2));
-            const uint32_t d0 = tmem_d + (uint32_t)(buf * kPartials * kBlk);
+            const uint64_t bd0 = b_desc0 + (uint64_t)((uint32_t)sb * kSlotUnits);
+            const uint32_t a0 = tmem_d + (uint32_t)(kAccCols + (q * kASlots + sa) * kACols);
 #pragma unroll
-            for (int j = 0; j < kKC / 16 && !(P.dbg & 1); ++j) {
-              // K-steps rotate over kPartials accumulators; the epilogue adds them up
-              umma_bf16_ts(d0 + (uint32_t)((j % kPartials) * kBlk), a0 + 8u * j, bd0 + (uint64_t)(j * kStepUnits), idesc,
-                           (cc > 0 || j >= kPartials) ? 1u : 0u);
-            }
-            umma_commit(&sm.a_empty[sa]);
-            if (!(P.dbg & 16)) umma_commit(&sm.b_empty[sb]);
-            if (cc == n_chunks - 1) umma_commit(&sm.acc_full[buf]);
+            for (int j = 0; j < kKC / 16 && !(P.dbg & 1); ++j)
+              umma_bf16_ts(d0, a0 + 8u * j, bd0 + (uint64_t)(j * kStepUnits), idesc, (cc >= kPipes || j > 0) ? 1u : 0u);
+            umma_commit(&sm.empty[q][sa]);
+            if (cc + kPipes >= n_chunks) umma_commit(&sm.acc_full[buf]);  // this pipeline's share of the block is in
           }
           __syncwarp();
-          TC_ACC(1);
-          if (++sa == kAStages) sa = 0;
-          if (++sb == kBStages) sb = 0;
+          if (q == 0) TC_NEXT(22);
+          if (++sa == kASlots) sa = 0;
+          if (++sb == kBSlots) sb = 0;
         }
       }
     }
@@ -469,26 +473,23 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
       {
         TC_T0();
         mbar_wait_backoff(&sm.acc_full[buf], (accf_phase >> buf) & 1u);
-        if (warp == 8) TC_ACC(8);
+        if (warp == kEpilogue0) TC_ACC(11);
       }
       accf_phase ^= 1u << buf;
       TC_T0();
       tc_fence_after();
       float h[kBlk];
-      tmem_ld32(tmem_lane + (uint32_t)(buf * kPartials * kBlk), h);
-#pragma unroll
-      for (int pp = 1; pp < kPartials; ++pp) {
+      tmem_ld32(tmem_lane + (uint32_t)(buf * kPipes * kBlk), h);
+      if (n_active > 1) {
         float hp[kBlk];
-        tmem_ld32(tmem_lane + (uint32_t)((buf * kPartials + pp) * kBlk), hp);
+        tmem_ld32(tmem_lane + (uint32_t)((buf * kPipes + 1) * kBlk), hp);
 #pragma unroll
         for (int i = 0; i < kBlk; ++i) h[i] += hp[i];
       }
       tc_fence_before();
-      mbar_arrive(&sm.acc_free[buf]);  // the tensor core may overwrite this buffer (block gb + 2)
-      if (P.bias) {
+      warp_arrive(&sm.acc_free[buf]);  // the tensor core may overwrite this buffer (block gb + 2)
 #pragma unroll
-        for (int i = 0; i < kBlk; ++i) h[i] += __ldg(P.bias + i0 + i);
-      }
+      for (int i = 0; i < kBlk; ++i) h[i] = fmaf(h[i], 0.5f, P.bias ? __ldg(P.bias + i0 + i) : 0.0f);  // spins were 0 / 2
       if (P.gemm_only) {
         if (P.fields_out && chain_ok) {
 #pragma unroll
@@ -502,19 +503,19 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
 #pragma unroll
         for (int i = 0; i < kBlk; ++i) {
           if (P.fields_out && chain_ok) P.fields_out[(size_t)chain * N + i0 + i] = h[i];  // field at visit time
-          const float d_up = ((w_old >> i) & 1u) ? 0.0f : 1.0f;   // new - old if the site comes out 1 ...
-          const float d_dn = d_up - 1.0f;                          // ... or 0 (both known before the chain)
+          const float d_up = ((w_old >> site_bit(i)) & 1u) ? 0.0f : 1.0f;   // new - old if the site comes out 1 ...
+          const float d_dn = d_up - 1.0f;                                    // ... or 0 (both known before the chain)
           const bool up = h[i] > thr[i];
           const float delta = up ? d_up : d_dn;
-          w_new |= up ? (1u << i) : 0u;
+          w_new |= up ? (1u << site_bit(i)) : 0u;
           // not yet visited sites of the block see the new value (rank-1 correction, branch free)
 #pragma unroll
           for (int ip = i + 1; ip < kBlk; ++ip) h[ip] = fmaf(sm.jblk[i][ip], delta, h[ip]);
         }
         sm.sbits[blk][row] = w_new;
       }
-      mbar_arrive(&sm.state_ready[gb & 3]);  // release: the producers may expand chunks holding this block
-      if (warp == 8) TC_ACC(9);
+      warp_arrive(&sm.state_ready[gb & 3]);  // release: the producers may expand chunks holding this block
+      if (warp == kEpilogue0) TC_ACC(12);
     }
     if (!P.gemm_only && chain_ok) {  // unpack the final bits of this chain
       for (int w = 0; w < N / 32; ++w) {
@@ -522,8 +523,8 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
         uint8_t* dst = P.state + (size_t)chain * N + 32 * w;
 #pragma unroll
         for (int b = 0; b < 32; b += 4) {
-          const uint32_t n4 = (x >> b) & 15u;
-          *reinterpret_cast<uint32_t*>(dst + b) = (n4 & 1u) | ((n4 & 2u) << 7) | ((n4 & 4u) << 14) | ((n4 & 8u) << 21);
+          const uint32_t e2 = x >> (b >> 1), o2 = x >> (16 + (b >> 1));
+          *reinterpret_cast<uint32_t*>(dst + b) = (e2 & 1u) | ((o2 & 1u) << 8) | ((e2 & 2u) << 15) | ((o2 & 2u) << 23);
         }
       }
     }
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
   // ---- teardown ----------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == kIssuer0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_d) : "memory");
   }
 }
@@ -567,16 +568,17 @@ extern "C" int tsu_dense_gibbs_tc_run(const void* d_J_bf16, const float* d_bias,
   P.sweep0 = sweep0;
   P.chain0 = chain0;
   P.gemm_only = 0;
+  if (const char* e = getenv("TSU_TC_DEBUG")) P.dbg = atoi(e);
   return launch_tc(P, tsu_stream(stream));
 }
 
 #ifdef TSU_TC_TIMING
 extern "C" int tsu_dense_tc_debug_timing(unsigned long long* h_out16, int reset) {
   if (reset) {
-    unsigned long long z[16] = {0};
+    unsigned long long z[32] = {0};
     return (int)cudaMemcpyToSymbol(g_tc_timing, z, sizeof z);
   }
-  return (int)cudaMemcpyFromSymbol(h_out16, g_tc_timing, sizeof(unsigned long long) * 16);
+  return (int)cudaMemcpyFromSymbol(h_out16, g_tc_timing, sizeof(unsigned long long) * 32);
 }
 #endif
 
