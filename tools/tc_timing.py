@@ -15,10 +15,13 @@ a.record(); _lib.call("tsu_dense_gibbs_tc_run", _lib.ptr(J), None, _lib.ptr(st),
 torch.cuda.synchronize()
 out = (ctypes.c_ulonglong * 32)(); f(out, 0)
 ms = a.elapsed_time(b); total_clk = ms * 1e-3 * 1.965e9
-names = ["issuer0 wait full", "issuer1 wait full", "issuers wait acc_free", "P0 wait empty", "P0 wait state_ready", "P0 load+expand+arrive",
-         "-", "P1 wait empty", "P1 wait state_ready", "P1 load+expand+arrive", "-", "EPI wait acc_full", "EPI ld+update", "-", "-", "-",
-         "P0w0 load_b issue", "P0w0 lds+alu+sttm issue", "P0w0 wait::st", "P0w0 cp.async.wait", "P0w0 fence+syncwarp+arrive", "issuer0 membar+fence", "issuer0 mma+commit+syncwarp"]
-nchunks = 2 * 128 * 32
+names = {0: "issuer wait full (per chunk)", 2: "issuer wait acc_free", 3: "P0 wait empty (per own chunk = 1/2)", 7: "P1 wait empty",
+         4: "P0w0 wait panel_done", 16: "P0w0 J tile cp.async issue", 17: "P0w0 lds+alu+sttm issue", 18: "P0w0 wait::st",
+         19: "P0w0 cp.async.wait_group 0", 20: "P0w0 fence+syncwarp+arrive", 21: "issuer membar+fence", 22: "issuer mma+commit+syncwarp",
+         23: "corr issuer wait delta_ready", 24: "corr issuer fence+mma+commit", 11: "EPI wait acc_full (per panel)",
+         13: "EPI wait corr_done (3 per panel)", 12: "EPI ld+update+delta (4 per panel)",
+         25: "EPI jblk staging + 2 named barriers", 26: "EPI thresholds", 27: "EPI waits", 28: "EPI ldtm", 29: "EPI scale+chain", 30: "EPI delta sttm+arrive"}
+nchunks = 2 * 32 * 32
 print(f"2 sweeps: {ms:.2f} ms = {total_clk:.3e} clk; chunks per CTA = {nchunks}; {total_clk/nchunks:.0f} clk/chunk")
-for i, n in enumerate(names):
-    print(f"  {n:22s} {out[i]:14d} clk  {100*out[i]/total_clk:6.1f}% of kernel   {out[i]/nchunks:8.1f} clk/chunk")
+for i, n in sorted(names.items()):
+    print(f"  {n:42s} {out[i]:14d} clk  {100*out[i]/total_clk:6.1f}% of kernel   {out[i]/nchunks:8.1f} clk/chunk  {out[i]/(nchunks/32):9.0f} clk/panel")

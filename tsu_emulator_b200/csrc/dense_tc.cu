@@ -5,26 +5,28 @@
 //     h_i = np.dot(coupling[i, :], state) + bias[i]                 tsu/gibbs.py:79-100
 // inside the sequential sweep of tsu/gibbs.py:128-162.
 //
-// Exact sequential Gibbs, blocked: the N sites are visited in index order in blocks of 64.  For a block
-// the fields of its 64 sites for 128 chains are one 128 x 64 x N GEMM  H = S . J[blk, :]^T  (S: current bits
-// as bf16 0/1, J: bf16, fp32 accumulation in TMEM) issued as tcgen05.mma instructions by one thread; the
-// epilogue thread of each chain then walks the 64 sites in order, draws the heat-bath bit from
-// sigmoid(h/T) and applies the rank-1 correction h_i' += J[i', i] * (new - old) to the not yet visited
-// sites of the block, which makes the result identical to a site-by-site sweep with the same fields.
+// Exact sequential Gibbs, blocked on two levels.  The N sites are visited in index order.
+//   * PANEL (128 sites): the fields of a panel's sites for 128 chains are one 128 x 128 x N GEMM
+//     H = S . J[panel, :]^T  (S: current bits as bf16, J: bf16, fp32 accumulation in TMEM), issued as
+//     tcgen05.mma M128 N128 K16 instructions by one thread.  The K-chunk that holds the previous panel is
+//     multiplied last, after that panel's update; all other chunks overlap with it.
+//   * BLOCK (32 sites, four per panel): the epilogue thread of each chain reads the block's 32 fields out of
+//     TMEM, walks the sites in order, draws the heat-bath bit and applies the rank-1 correction
+//     h_i' += J[i', i] * (new - old) to the not yet visited sites of the block in registers.  The flips of the
+//     block are then written to TMEM as a 128 x 32 operand (-1 / 0 / +1) and ONE small MMA
+//     H[:, later blocks of the panel] += delta . J[later, block]^T  corrects the rest of the panel.
+// The result is identical to a site-by-site sweep with the same fields.
 //
 // One CTA owns 128 chains (TMEM lane = chain).  The chain states stay resident in shared memory as bits
 // for the whole sweep (64 KB).  Each K-chunk of 128 sites is expanded to bf16 by the thread that owns the
 // chain and written straight into TENSOR MEMORY (tcgen05.st, lane = chain, column = K pair): the spin
 // operand A never touches shared memory.  A spin is encoded as 0.0 / 2.0: bf16 2.0 = 0x4000 has ONE set bit,
 // so a packed pair of spins is (word << s) & 0x40004000 - two integer instructions per register - and the
-// accumulated field is halved (exactly) in the epilogue.  The matching J tile (operand B, K-major, no
-// swizzle) is streamed from L2 with cp.async.
-//
-// The K-chunks of a block alternate between two independent pipelines (producer group of 4 warps + one MMA
-// issuer warp + own operand rings + own accumulator), so that the per-chunk synchronisation latencies
-// (mbarrier wake-ups, TMEM store drain, commit) of one pipeline hide behind the other.
+// accumulated field is halved (exactly) in the epilogue.  The matching J tile (operand B, 128 x 128, K-major,
+// no swizzle) is streamed from L2 with cp.async.
 
 #include <cstdlib>
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -33,16 +35,16 @@
 namespace {
 
 constexpr int kChains = 128;  // chains per CTA = UMMA M = TMEM lanes
-constexpr int kBlk = 32;      // sites per block = UMMA N
+constexpr int kBlk = 32;      // sites per block (sequential update unit of the epilogue)
 constexpr int kKC = 128;      // K-chunk (sites) per pipeline stage
-constexpr int kPipes = 2;     // independent producer/issuer pipelines; chunk cc of a block goes to pipeline cc % kPipes
-constexpr int kASlots = 3;    // per pipeline: expanded spin tiles in tensor memory (64 columns each)
-constexpr int kLook = 4;      // per pipeline: J tiles are requested 4 of its own chunks ahead
-constexpr int kBSlots = kLook + kASlots;  // per pipeline: J tile ring (8 KB each).  With this depth the J slot of chunk
-                                          // m + kLook is the one chunk m - kASlots used: ONE "empty" barrier frees both
-constexpr int kAccCols = 2 * kPipes * kBlk;  // two buffers x one 32-column fp32 accumulator per pipeline = 128 columns
+constexpr int kPanel = 128;   // sites per panel = UMMA N of the main GEMM; a panel is also exactly one K-chunk
+constexpr int kStages = 3;    // ring: expanded spin tile in tensor memory (64 columns) + J tile in shared memory (32 KB)
+constexpr int kGroups = 2;    // producer groups: chunk g of the global sequence goes to group g % kGroups
 constexpr int kACols = kKC / 2;              // 32-bit columns of one expanded spin tile
-static_assert(kAccCols + kPipes * kASlots * kACols <= 512, "tensor memory budget");
+constexpr int kAccCols = 2 * kPanel;         // two panel accumulators (fp32, 128 columns each)
+constexpr int kDeltaCol = kAccCols + kStages * kACols;  // 16 columns: flips of one block as bf16 pairs
+static_assert(kDeltaCol + kBlk / 2 <= 512, "tensor memory budget");
+static_assert(kPanel == kKC && kPanel == 4 * kBlk, "panel = chunk = four blocks");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -55,6 +57,18 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
   return d;                // base offset 0, layout type 0 = SWIZZLE_NONE
+}
+
+// same for the 128-byte swizzled K-major layout TMA writes (rows of 64 bf16 = 128 bytes, 8-row groups of 1024 bytes):
+// SBO = 1024, LBO unused, layout type 2 = SWIZZLE_128B; a K = 16 step advances the start address by 32 bytes
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
 }
 
 // instruction descriptor: D = F32, A = B = BF16, both K-major, M x N
@@ -107,6 +121,18 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// one 64 x 128 box (K x rows) of the bf16 matrix behind `tmap` -> 16 KB of shared memory, completion on `bar`
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(smem)),
+      "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
 }
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -193,25 +219,36 @@ struct TcParams {
   int dbg;                  // diagnostics (TSU_TC_DEBUG, timing experiments only): 1 no MMA, 2 no A expansion, 4 no J loads
 };
 
-constexpr int kProducers = 128 * kPipes;            // warps 0-7: 4 warps (128 chains) per pipeline
+constexpr int kProducers = 128 * kGroups;           // warps 0-7: 4 warps (128 chains) per group
 constexpr int kEpilogue0 = kProducers / 32;         // warps 8-11: epilogue (thread = chain = TMEM lane)
-constexpr int kIssuer0 = kEpilogue0 + 4;            // warps 12-13: MMA issuers
-constexpr int kThreads = 32 * (kIssuer0 + kPipes);  // 448
+constexpr int kIssuer0 = kEpilogue0 + 4;            // warp 12: main GEMM issuer, warp 13: in-panel correction issuer
+constexpr int kThreads = 32 * (kIssuer0 + 2);       // 448
 
 // position of site i (0-31 of a block) inside a state word: even sites in the low half, odd sites in the high
 // half, so that (word >> j) & 0x00010001 is the pair (2j, 2j+1)
 __host__ __device__ constexpr int site_bit(int i) { return (i >> 1) + 16 * (i & 1); }
 
-// shared memory carve-up (~182 KB)
+// J tile in shared memory as TMA writes it: two K halves of 64 sites, each 128 rows (sites n) x 128 bytes, 128-byte swizzle
+constexpr int kTileBytes = kPanel * kKC * 2;   // 32 KB
+constexpr int kHalfBytes = kTileBytes / 2;     // one TMA box
+struct __align__(1024) JTile {
+  unsigned char bytes[kTileBytes];
+};
+
+// shared memory carve-up (~197 KB; the J tiles need 1024-byte alignment for the swizzle)
 struct TcSmem {
   uint32_t sbits[4096 / 32][kChains];        // chain states, word-major: sbits[w][chain], bit order = site_bit()
-  __align__(128) __nv_bfloat16 b[kPipes][kBSlots][kKC / 8][kBlk / 8][8][8];
+  JTile b[kStages];                          // J[panel rows, chunk columns]
+  JTile jdiag;                               // J[panel rows, panel columns]: operand of the in-panel corrections
   __align__(16) float jblk[kBlk][kBlk + 4];  // J[blk, blk] as fp32, transposed: jblk[i][i'] = J[i0+i'][i0+i]
-  __align__(8) uint64_t full[kPipes][kASlots];   // producers -> issuer: A slot written, J tile landed  (one arrival per warp)
-  __align__(8) uint64_t empty[kPipes][kASlots];  // issuer -> producers: the MMAs reading the A slot (and its J slot) are done (commit)
-  __align__(8) uint64_t acc_full[2];         // issuers -> epilogue: accumulator buffer complete          (one commit per pipeline)
-  __align__(8) uint64_t acc_free[2];         // epilogue -> issuers: accumulator buffer read out          (one arrival per warp)
-  __align__(8) uint64_t state_ready[4];      // epilogue -> producers: bits of block gb written (ring, one arrival per warp)
+  __align__(8) uint64_t full[kStages];       // producers -> issuer: A slot written (one arrival per warp) + J tile landed (TMA bytes)
+  __align__(8) uint64_t empty[kStages];      // issuer -> producers: the MMAs reading the stage are done        (commit)
+  __align__(8) uint64_t acc_full[2];         // issuer -> epilogue: main GEMM of the panel complete             (commit)
+  __align__(8) uint64_t acc_free[2];         // epilogue -> issuer: accumulator buffer read out     (one arrival per warp)
+  __align__(8) uint64_t panel_done[4];       // epilogue -> producers: bits of panel gp written (ring, one arrival per warp)
+  __align__(8) uint64_t delta_ready;         // epilogue -> correction issuer: flips of a block are in TMEM (per warp)
+  __align__(8) uint64_t jdiag_full;          // TMA -> correction issuer: jdiag of the panel landed
+  __align__(8) uint64_t corr_done;           // correction issuer -> epilogue: the rest of the panel is corrected (commit)
   uint32_t tmem_base;
 };
 
@@ -227,15 +264,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
+__global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // round the base up to 1024 bytes in the SHARED address space (keeps the compiler on LDS/STS)
+  TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tid >> 5;
   const int N = P.N;
-  const int n_blocks = N / kBlk, n_chunks = N / kKC;
-  const int total_blocks = n_blocks * P.n_sweeps;
-  const int n_active = n_chunks < kPipes ? n_chunks : kPipes;  // pipelines that ever get a chunk
-  static_assert(kKC == 4 * kBlk, "a K-chunk holds four blocks");
+  const int n_panels = N / kPanel;  // = number of K-chunks
+  const int total_panels = n_panels * P.n_sweeps;
 
   // ---- one-time setup -------------------------------------------------------------------------
   if (tid < kChains) {  // pack this chain's bits
@@ -255,16 +291,18 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
     }
   }
   if (tid == 0) {
-    for (int q = 0; q < kPipes; ++q)
-      for (int s = 0; s < kASlots; ++s) {
-        mbar_init(&sm.full[q][s], 4);
-        mbar_init(&sm.empty[q][s], 1);
-      }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&sm.full[s], 5);
+      mbar_init(&sm.empty[s], 1);
+    }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&sm.acc_full[s], n_active);
+      mbar_init(&sm.acc_full[s], 1);
       mbar_init(&sm.acc_free[s], 4);
     }
-    for (int s = 0; s < 4; ++s) mbar_init(&sm.state_ready[s], 4);
+    for (int s = 0; s < 4; ++s) mbar_init(&sm.panel_done[s], 4);
+    mbar_init(&sm.delta_ready, 4);
+    mbar_init(&sm.corr_done, 1);
+    mbar_init(&sm.jdiag_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kIssuer0) {
@@ -277,73 +315,42 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
   const uint32_t tmem_d = sm.tmem_base;
 
   if (warp < kEpilogue0) {
-    // ===================== producers: expand spins to bf16 A tiles, stream J tiles ======================
-    // pipeline q = warp / 4 handles the chunks cc = q, q + kPipes, ... of every block; thread = chain (TMEM lane)
+    // ===================== producers: stream J tiles, expand spins to bf16 A tiles ======================
+    // group q = warp / 4 handles the chunks g = q, q + kGroups, ... of the global sequence (panel-major);
+    // thread = chain (TMEM lane)
     const int q = warp >> 2, row = tid & (kChains - 1);
-    if (q < n_active) {
-      // J tile requests run kLook of the pipeline's own chunks ahead (across blocks and sweeps)
-      int ld_gb = 0, ld_blk = 0, ld_cc = q, ld_slot = 0;
-      auto load_b = [&]() {
-        if (ld_gb < total_blocks) {
-          int lkc = ld_cc + (ld_blk >> 2) + 1;
-          if (lkc >= n_chunks) lkc -= n_chunks;
-          const __nv_bfloat16* src = P.J + (size_t)(ld_blk * kBlk) * N + lkc * kKC;
-          // 16-byte pieces: a warp instruction covers 16 rows x one 32-byte sector (full sectors from L2) and lands
-          // in two 256-byte runs of the tile (4 shared-memory wavefronts, the minimum for 512 bytes)
-          if (!(P.dbg & 4)) {
-#pragma unroll
-            for (int p = 0; p < kBlk * (kKC / 8) / kChains; ++p) {
-              const int n = ((row & 31) >> 1) + 16 * (p & 1), k16 = 2 * ((row >> 5) + 4 * (p >> 1)) + (row & 1);
-              cp_async16(&sm.b[q][ld_slot][k16][n >> 3][n & 7][0], src + (size_t)n * N + 8 * k16);
-            }
-          }
-          if (++ld_slot == kBSlots) ld_slot = 0;
-          ld_cc += kPipes;
-          if (ld_cc >= n_chunks) {
-            ld_cc = q;
-            ++ld_gb;
-            if (++ld_blk == n_blocks) ld_blk = 0;
-          }
-        }
-        cp_async_commit();  // (an empty group at the tail keeps the group count uniform)
-      };
-      for (int i = 0; i < kLook; ++i) load_b();
-      uint32_t empty_phase = 0;
-      int ready_seen = 0;  // number of state_ready phases consumed (block gb needs gb of them for its last two chunks)
-      int sa = 0;
-      long long m = 0;     // own chunks done
-      for (int gb = 0; gb < total_blocks; ++gb) {
-        const int blk = gb % n_blocks;
-        for (int cc = q; cc < n_chunks; cc += kPipes, ++m) {
-          // chunk order: own + 1, ..., own - 1, own.  The two last chunks may hold the previous block's sites,
-          // so they wait for that block's update; everything earlier only needs older state.
-          int kc = cc + (blk >> 2) + 1;
-          if (kc >= n_chunks) kc -= n_chunks;
-          if (m >= kASlots) {  // the MMAs of own chunk m - kASlots are done: A slot sa and the J slot of chunk m + kLook are free
+    int done_seen = 0;  // number of panel_done phases consumed
+    long long g = 0;
+    int s = 0;          // stage of chunk g
+    uint32_t round = 0; // g / kStages: how often the ring has wrapped
+    for (int gp = 0; gp < total_panels; ++gp) {
+      const int p = gp % n_panels;
+      for (int cc = 0; cc < n_panels; ++cc, ++g) {
+        if ((int)(g % kGroups) == q) {
+          // chunk order: own, own + 1, ..., own - 2 and LAST own - 1, the previous panel, which has to be
+          // updated first; everything earlier only needs the state as of two panels ago
+          int kc = p + cc;
+          if (kc >= n_panels) kc -= n_panels;
+          if (round > 0) {  // the MMAs of chunk g - kStages (the other group's, for an odd ring) are done: the stage is free
             TC_T0();
-            mbar_wait(&sm.empty[q][sa], (empty_phase >> sa) & 1u);
-            empty_phase ^= 1u << sa;
+            mbar_wait(&sm.empty[s], (round - 1u) & 1u);  // completion number `round` of this stage's barrier
             if ((warp & 3) == 0) TC_ACC(3 + 4 * q);
           }
-#ifdef TSU_TC_TIMING
-          long long tl0__ = clock64();
-#endif
-          load_b();
-#ifdef TSU_TC_TIMING
-          if (warp == 0 && blockIdx.x == 0 && (tid & 31) == 0) atomicAdd(&g_tc_timing[16], (unsigned long long)(clock64() - tl0__));
-#endif
-          const int need = (cc >= n_chunks - 2) ? gb : gb - 1;
-          if (ready_seen < need) {
-            TC_T0();
-            while (ready_seen < need) {
-              mbar_wait(&sm.state_ready[ready_seen & 3], (uint32_t)((ready_seen >> 2) & 1));
-              ++ready_seen;
-            }
-            if ((warp & 3) == 0) TC_ACC(4 + 4 * q);
-          }
           TC_T0();
+          if (row == 0) {  // J[panel p rows, chunk kc columns]: two 16 KB boxes, bytes counted on the stage's full barrier
+            mbar_arrive_expect_tx(&sm.full[s], kTileBytes);
+            tma_load_2d(sm.b[s].bytes, &tmap, kc * kKC, p * kPanel, &sm.full[s]);
+            tma_load_2d(sm.b[s].bytes + kHalfBytes, &tmap, kc * kKC + 64, p * kPanel, &sm.full[s]);
+          }
+          if (warp == 0) TC_NEXT(16);
+          const int need = (cc == n_panels - 1) ? gp : gp - 1;
+          while (done_seen < need) {
+            mbar_wait(&sm.panel_done[done_seen & 3], (uint32_t)((done_seen >> 2) & 1));
+            ++done_seen;
+          }
+          if (warp == 0) TC_NEXT(4);
           // 128 bits of this chain -> 64 packed bf16 pairs -> 64 TMEM columns of the chain's lane
-          const uint32_t a_col = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kAccCols + (q * kASlots + sa) * kACols);
+          const uint32_t a_col = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kAccCols + s * kACols);
 #pragma unroll
           for (int w4 = 0; w4 < kKC / 32 && !(P.dbg & 2); ++w4) {
             const uint32_t w = sm.sbits[(kKC / 32) * kc + w4][row];
@@ -356,77 +363,97 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
           if (warp == 0) TC_NEXT(17);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           if (warp == 0) TC_NEXT(18);
-          cp_async_wait<kLook>();  // this thread's pieces of the J tile of this chunk have landed
-          if (warp == 0) TC_NEXT(19);
-          // NOTE: no fence.proxy.async here.  It lowers to MEMBAR.ALL.CTA, which waits for ALL of the thread's
-          // outstanding memory operations - including the J-tile cp.asyncs just issued for kLook chunks ahead -
-          // i.e. one full L2/HBM latency per chunk.  The issuer warp executes the proxy fence after its acquire.
           tc_fence_before();
-          warp_arrive(&sm.full[q][sa]);
+          warp_arrive(&sm.full[s]);
           if (warp == 0) TC_NEXT(20);
-          if (warp == 4) TC_ACC(9);
-          if (++sa == kASlots) sa = 0;
+        }
+        if (++s == kStages) {
+          s = 0;
+          ++round;
         }
       }
     }
-  } else if (warp >= kIssuer0) {
-    // ===================== MMA issuers: one elected lane per pipeline feeds the tensor core ================
+  } else if (warp == kIssuer0) {
+    // ===================== main GEMM issuer: one elected lane feeds the tensor core ======================
     // The whole warp runs the loop (uniform control flow keeps counters and descriptors in uniform registers);
     // only the tcgen05.mma / commit instructions are issued by the elected lane.
-    const int q = warp - kIssuer0;
-    if (q < n_active) {
-      const uint32_t idesc = umma_idesc(kChains, kBlk);
-      constexpr uint32_t kLbo = (kBlk / 8) * 128, kSbo = 128;
-      const uint64_t b_desc0 = umma_desc(smem_u32(&sm.b[q][0][0][0][0][0]), kLbo, kSbo);
-      constexpr uint32_t kSlotUnits = (uint32_t)(sizeof(sm.b[0][0]) >> 4);  // 16-byte units per ring slot
-      constexpr uint32_t kStepUnits = (2 * kLbo) >> 4;                       // per K = 16 step
-      uint32_t full_phase = 0, free_phase = 0;
-      int sa = 0, sb = 0;
-      for (int gb = 0; gb < total_blocks; ++gb) {
-        const int buf = gb & 1;
-        if (gb >= 2) {  // the epilogue has read this accumulator buffer out
+    const uint32_t idesc = umma_idesc(kChains, kPanel);
+    const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sm.b[0].bytes));
+    constexpr uint32_t kSlotUnits = (uint32_t)(kTileBytes >> 4);  // 16-byte units per ring slot
+    uint32_t full_phase = 0, free_phase = 0;
+    int s = 0;
+    for (int gp = 0; gp < total_panels; ++gp) {
+      const int buf = gp & 1;
+      if (gp >= 2) {  // the epilogue has read this accumulator buffer out
+        TC_T0();
+        mbar_wait(&sm.acc_free[buf], (free_phase >> buf) & 1u);
+        free_phase ^= 1u << buf;
+        TC_ACC(2);
+      }
+      const uint32_t d0 = tmem_d + (uint32_t)(buf * kPanel);
+      for (int cc = 0; cc < n_panels; ++cc) {
+        {
           TC_T0();
-          mbar_wait(&sm.acc_free[buf], (free_phase >> buf) & 1u);
-          free_phase ^= 1u << buf;
-          TC_ACC(2);
+          mbar_wait(&sm.full[s], (full_phase >> s) & 1u);
+          TC_ACC(0);
         }
-        const uint32_t d0 = tmem_d + (uint32_t)((buf * kPipes + q) * kBlk);
-        for (int cc = q; cc < n_chunks; cc += kPipes) {
-          {
-            TC_T0();
-            mbar_wait(&sm.full[q][sa], (full_phase >> sa) & 1u);
-            TC_ACC(q);
-          }
-          full_phase ^= 1u << sa;
-          TC_T0();
-          fence_async_smem();  // producers' cp.async (generic proxy) writes, acquired above -> async proxy reads
-          tc_fence_after();
-          if (q == 0) TC_NEXT(21);
-          if (elect_one()) {
-            const uint64_t bd0 = b_desc0 + (uint64_t)((uint32_t)sb * kSlotUnits);
-            const uint32_t a0 = tmem_d + (uint32_t)(kAccCols + (q * kASlots + sa) * kACols);
+        full_phase ^= 1u << s;
+        TC_T0();
+        tc_fence_after();
+        TC_NEXT(21);
+        if (elect_one()) {
+          const uint64_t bd0 = b_desc0 + (uint64_t)((uint32_t)s * kSlotUnits);
+          const uint32_t a0 = tmem_d + (uint32_t)(kAccCols + s * kACols);
 #pragma unroll
-            for (int j = 0; j < kKC / 16 && !(P.dbg & 1); ++j)
-              umma_bf16_ts(d0, a0 + 8u * j, bd0 + (uint64_t)(j * kStepUnits), idesc, (cc >= kPipes || j > 0) ? 1u : 0u);
-            umma_commit(&sm.empty[q][sa]);
-            if (cc + kPipes >= n_chunks) umma_commit(&sm.acc_full[buf]);  // this pipeline's share of the block is in
+          for (int j = 0; j < kKC / 16 && !(P.dbg & 1); ++j)
+            umma_bf16_ts(d0, a0 + 8u * j, bd0 + (uint64_t)(((j >> 2) * kHalfBytes + (j & 3) * 32) >> 4), idesc,
+                         (cc > 0 || j > 0) ? 1u : 0u);
+          umma_commit(&sm.empty[s]);
+          if (cc == n_panels - 1) umma_commit(&sm.acc_full[buf]);
+        }
+        __syncwarp();
+        TC_NEXT(22);
+        if (++s == kStages) s = 0;
+      }
+    }
+  } else if (warp == kIssuer0 + 1) {
+    // ===================== correction issuer: H[:, later blocks] += delta(block b) . J[later, block b]^T ====
+    if (!P.gemm_only) {
+      const uint64_t jd_desc0 = umma_desc_sw128(smem_u32(sm.jdiag.bytes));
+      uint32_t ready_phase = 0;
+      for (int gp = 0; gp < total_panels; ++gp) {
+        const uint32_t d0 = tmem_d + (uint32_t)((gp & 1) * kPanel);
+        for (int b = 0; b < 3; ++b) {
+          TC_T0();
+          mbar_wait(&sm.delta_ready, ready_phase);
+          ready_phase ^= 1u;
+          if (b == 0) mbar_wait(&sm.jdiag_full, (uint32_t)(gp & 1));  // J[panel, panel] has landed
+          TC_NEXT(23);
+          tc_fence_after();
+          if (elect_one()) {
+            const int n_cols = kPanel - kBlk * (b + 1);               // columns (sites) of the blocks still to come
+            const uint32_t idesc = umma_idesc(kChains, n_cols);
+            // rows (sites) 32 (b+1) .. 127 of jdiag (8-row groups of 1024 bytes), K = sites 32 b .. 32 b + 31 of the panel
+            const uint64_t bd = jd_desc0 + (uint64_t)(((uint32_t)(b >> 1) * kHalfBytes + (uint32_t)(4 * (b + 1)) * 1024u + (uint32_t)(b & 1) * 64u) >> 4);
+#pragma unroll
+            for (int j = 0; j < kBlk / 16; ++j)
+              umma_bf16_ts(d0 + (uint32_t)(kBlk * (b + 1)), tmem_d + (uint32_t)(kDeltaCol + 8 * j), bd + (uint64_t)(2 * j), idesc, 1u);
+            umma_commit(&sm.corr_done);
           }
           __syncwarp();
-          if (q == 0) TC_NEXT(22);
-          if (++sa == kASlots) sa = 0;
-          if (++sb == kBSlots) sb = 0;
+          TC_NEXT(24);
         }
       }
     }
   } else {
-    // ===================== epilogue: fields out of TMEM, sequential update of the block ================
+    // ===================== epilogue: fields out of TMEM, sequential update block by block ================
     const int row = tid - kProducers;                    // TMEM lane = chain within the tile
     const int chain = blockIdx.x * kChains + row;
     const bool chain_ok = chain < P.n_chains;
     const uint32_t tmem_lane = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
     const float T = P.T_chain ? (float)P.T_chain[chain_ok ? chain : 0] : P.T;
     const uint32_t chain_g = P.chain0 + (uint32_t)chain;
-    uint32_t accf_phase = 0;
+    uint32_t accf_phase = 0, corr_phase = 0;
     // diagonal block J[blk, blk]: 8 bf16 per thread (row i0 + row/4, columns i0 + 8 (row%4) ..), fetched one
     // block ahead so that the load latency hides behind the previous block's update
     auto load_diag = [&](int blk) {
@@ -434,88 +461,123 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
       return __ldg(reinterpret_cast<const uint4*>(P.J + (size_t)(i0 + (row >> 2)) * N + i0 + 8 * (row & 3)));
     };
     uint4 jd = load_diag(0);
-    for (int gb = 0; gb < total_blocks; ++gb) {
-      const int blk = gb % n_blocks, sweep = gb / n_blocks, buf = gb & 1;
-      const int i0 = blk * kBlk;
-      // diagonal block as fp32, transposed: jblk[i][i'] = J[i0 + i', i0 + i]
-      named_bar_sync(1, kChains);  // everybody is done with the previous block's jblk
-      {
-        const uint32_t jw[4] = {jd.x, jd.y, jd.z, jd.w};
-        const int r = row >> 2, c0 = 8 * (row & 3);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          sm.jblk[c0 + 2 * e][r] = __uint_as_float(jw[e] << 16);  // bf16 -> fp32 is a 16-bit shift
-          sm.jblk[c0 + 2 * e + 1][r] = __uint_as_float(jw[e] & 0xffff0000u);
-        }
+    const int n_blocks = N / kBlk;
+    for (int gp = 0; gp < total_panels; ++gp) {
+      const int p = gp % n_panels, sweep = gp / n_panels, buf = gp & 1;
+      // J[panel, panel] for this panel's corrections; the previous panel's corrections are all complete
+      if (!P.gemm_only && row == 0) {
+        mbar_arrive_expect_tx(&sm.jdiag_full, kTileBytes);
+        tma_load_2d(sm.jdiag.bytes, &tmap, p * kPanel, p * kPanel, &sm.jdiag_full);
+        tma_load_2d(sm.jdiag.bytes + kHalfBytes, &tmap, p * kPanel + 64, p * kPanel, &sm.jdiag_full);
       }
-      if (gb + 1 < total_blocks) jd = load_diag((gb + 1) % n_blocks);
-      named_bar_sync(1, kChains);
-      // Acceptance thresholds of the block, computed while the tensor core is still accumulating:
-      //   u < sigmoid(h / T)  <=>  h > T * logit(u)          (gibbs.py:61-77,126; strict <)
-      // and the clamp of gibbs.py:65-70 (|h/T| > 20 -> p = 1 / 0) is the clamp of the threshold to +-20 T.
-      // This takes exp, the division and the Philox call off the site-to-site dependency chain: per site the
-      // chain is compare -> select -> fma.
-      float thr[kBlk];
-      if (!P.gemm_only) {
+      for (int b = 0; b < 4; ++b) {
+        const int blk = 4 * p + b, i0 = blk * kBlk;
+#ifdef TSU_TC_TIMING
+        long long tb__ = clock64();
+#define TC_B(i) do { const long long t1__ = clock64(); if (blockIdx.x == 0 && tid == kProducers) atomicAdd(&g_tc_timing[i], (unsigned long long)(t1__ - tb__)); tb__ = t1__; } while (0)
+#else
+#define TC_B(i) do {} while (0)
+#endif
+        // diagonal block as fp32, transposed: jblk[i][i'] = J[i0 + i', i0 + i]
+        named_bar_sync(1, kChains);  // everybody is done with the previous block's jblk
+        {
+          const uint32_t jw[4] = {jd.x, jd.y, jd.z, jd.w};
+          const int r = row >> 2, c0 = 8 * (row & 3);
 #pragma unroll
-        for (int i = 0; i < kBlk; i += 4) {
-          const tsu_u32x4 o = tsu_philox4x32_10((uint32_t)((i0 + i) >> 2), chain_g, P.sweep0 + (uint32_t)sweep,
-                                                TSU_STREAM_DENSE_TC, P.k0, P.k1);
-          const uint32_t r4[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float u = (float)(r4[k] >> 8) * (1.0f / 16777216.0f);  // 24-bit uniform, exact in fp32
-            const float lg = (__log2f(u) - __log2f(1.0f - u)) * 0.69314718056f;
-            thr[i + k] = fminf(fmaxf(lg, -20.0f), 20.0f) * T;
+          for (int e = 0; e < 4; ++e) {
+            sm.jblk[c0 + 2 * e][r] = __uint_as_float(jw[e] << 16);  // bf16 -> fp32 is a 16-bit shift
+            sm.jblk[c0 + 2 * e + 1][r] = __uint_as_float(jw[e] & 0xffff0000u);
           }
         }
-      }
-      {
+        jd = load_diag((blk + 1) % n_blocks);
+        named_bar_sync(1, kChains);
+        TC_B(25);
+        // Acceptance thresholds of the block, computed while the tensor core is still busy:
+        //   u < sigmoid(h / T)  <=>  h > T * logit(u)          (gibbs.py:61-77,126; strict <)
+        // and the clamp of gibbs.py:65-70 (|h/T| > 20 -> p = 1 / 0) is the clamp of the threshold to +-20 T.
+        // This takes exp, the division and the Philox call off the site-to-site dependency chain: per site the
+        // chain is compare -> select -> fma.
+        float thr[kBlk];
+        if (!P.gemm_only) {
+#pragma unroll
+          for (int i = 0; i < kBlk; i += 4) {
+            const tsu_u32x4 o = tsu_philox4x32_10((uint32_t)((i0 + i) >> 2), chain_g, P.sweep0 + (uint32_t)sweep,
+                                                  TSU_STREAM_DENSE_TC, P.k0, P.k1);
+            const uint32_t r4[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float u = (float)(r4[k] >> 8) * (1.0f / 16777216.0f);  // 24-bit uniform, exact in fp32
+              const float lg = (__log2f(u) - __log2f(1.0f - u)) * 0.69314718056f;
+              thr[i + k] = fminf(fmaxf(lg, -20.0f), 20.0f) * T;
+            }
+          }
+        }
+        TC_B(26);
+        {
+          TC_T0();
+          if (b == 0) {
+            mbar_wait_backoff(&sm.acc_full[buf], (accf_phase >> buf) & 1u);  // main GEMM of the panel
+            accf_phase ^= 1u << buf;
+            if (warp == kEpilogue0) TC_ACC(11);
+          } else if (!P.gemm_only) {
+            mbar_wait(&sm.corr_done, corr_phase);  // flips of block b - 1 are in the fields of this block
+            corr_phase ^= 1u;
+            if (warp == kEpilogue0) TC_ACC(13);
+          }
+        }
         TC_T0();
-        mbar_wait_backoff(&sm.acc_full[buf], (accf_phase >> buf) & 1u);
-        if (warp == kEpilogue0) TC_ACC(11);
-      }
-      accf_phase ^= 1u << buf;
-      TC_T0();
-      tc_fence_after();
-      float h[kBlk];
-      tmem_ld32(tmem_lane + (uint32_t)(buf * kPipes * kBlk), h);
-      if (n_active > 1) {
-        float hp[kBlk];
-        tmem_ld32(tmem_lane + (uint32_t)((buf * kPipes + 1) * kBlk), hp);
-#pragma unroll
-        for (int i = 0; i < kBlk; ++i) h[i] += hp[i];
-      }
-      tc_fence_before();
-      warp_arrive(&sm.acc_free[buf]);  // the tensor core may overwrite this buffer (block gb + 2)
-#pragma unroll
-      for (int i = 0; i < kBlk; ++i) h[i] = fmaf(h[i], 0.5f, P.bias ? __ldg(P.bias + i0 + i) : 0.0f);  // spins were 0 / 2
-      if (P.gemm_only) {
-        if (P.fields_out && chain_ok) {
-#pragma unroll
-          for (int i = 0; i < kBlk; ++i) P.fields_out[(size_t)chain * N + i0 + i] = h[i];
+        TC_B(27);
+        tc_fence_after();
+        float h[kBlk];
+        tmem_ld32(tmem_lane + (uint32_t)(buf * kPanel + b * kBlk), h);
+        TC_B(28);
+        if (b == 3) {
+          tc_fence_before();
+          warp_arrive(&sm.acc_free[buf]);  // the tensor core may overwrite this buffer (panel gp + 2)
         }
-      } else {
-        // sequential heat-bath update of the 32 sites of this block for this thread's chain (gibbs.py:153-160)
-        static_assert(kBlk == 32, "one state word per block");
-        const uint32_t w_old = sm.sbits[blk][row];
-        uint32_t w_new = 0;
 #pragma unroll
-        for (int i = 0; i < kBlk; ++i) {
-          if (P.fields_out && chain_ok) P.fields_out[(size_t)chain * N + i0 + i] = h[i];  // field at visit time
-          const float d_up = ((w_old >> site_bit(i)) & 1u) ? 0.0f : 1.0f;   // new - old if the site comes out 1 ...
-          const float d_dn = d_up - 1.0f;                                    // ... or 0 (both known before the chain)
-          const bool up = h[i] > thr[i];
-          const float delta = up ? d_up : d_dn;
-          w_new |= up ? (1u << site_bit(i)) : 0u;
-          // not yet visited sites of the block see the new value (rank-1 correction, branch free)
+        for (int i = 0; i < kBlk; ++i) h[i] = fmaf(h[i], 0.5f, P.bias ? __ldg(P.bias + i0 + i) : 0.0f);  // spins were 0 / 2
+        if (P.gemm_only) {
+          if (P.fields_out && chain_ok) {
 #pragma unroll
-          for (int ip = i + 1; ip < kBlk; ++ip) h[ip] = fmaf(sm.jblk[i][ip], delta, h[ip]);
+            for (int i = 0; i < kBlk; ++i) P.fields_out[(size_t)chain * N + i0 + i] = h[i];
+          }
+        } else {
+          // sequential heat-bath update of the 32 sites of this block for this thread's chain (gibbs.py:153-160)
+          static_assert(kBlk == 32, "one state word per block");
+          const uint32_t w_old = sm.sbits[blk][row];
+          uint32_t w_new = 0;
+#pragma unroll
+          for (int i = 0; i < kBlk; ++i) {
+            if (P.fields_out && chain_ok) P.fields_out[(size_t)chain * N + i0 + i] = h[i];  // field at visit time
+            const float d_up = ((w_old >> site_bit(i)) & 1u) ? 0.0f : 1.0f;   // new - old if the site comes out 1 ...
+            const float d_dn = d_up - 1.0f;                                    // ... or 0 (both known before the chain)
+            const bool up = h[i] > thr[i];
+            const float delta = up ? d_up : d_dn;
+            w_new |= up ? (1u << site_bit(i)) : 0u;
+            // not yet visited sites of the block see the new value (rank-1 correction, branch free)
+#pragma unroll
+            for (int ip = i + 1; ip < kBlk; ++ip) h[ip] = fmaf(sm.jblk[i][ip], delta, h[ip]);
+          }
+          sm.sbits[blk][row] = w_new;
+          TC_B(29);
+          if (b < 3) {
+            // flips of the block as a bf16 operand in the accumulator's units (spins are 0 / 2): +2 = 0x4000, -2 = 0xC000
+            const uint32_t chg = w_new ^ w_old, neg = w_old & ~w_new;
+            uint32_t r[16];
+#pragma unroll
+            for (int j = 0; j < 15; ++j) r[j] = ((chg << (14 - j)) & 0x40004000u) | ((neg << (15 - j)) & 0x80008000u);
+            r[15] = ((chg >> 1) & 0x40004000u) | (neg & 0x80008000u);
+            tmem_st16(tmem_lane + (uint32_t)kDeltaCol, r);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            warp_arrive(&sm.delta_ready);
+            TC_B(30);
+          }
         }
-        sm.sbits[blk][row] = w_new;
+        if (warp == kEpilogue0) TC_ACC(12);
       }
-      warp_arrive(&sm.state_ready[gb & 3]);  // release: the producers may expand chunks holding this block
-      if (warp == kEpilogue0) TC_ACC(12);
+      warp_arrive(&sm.panel_done[gp & 3]);  // release: the producers may expand the chunk holding this panel
     }
     if (!P.gemm_only && chain_ok) {  // unpack the final bits of this chain
       for (int w = 0; w < N / 32; ++w) {
@@ -539,11 +601,38 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P) {
 
 }  // namespace
 
+// 2-D tensor map of the bf16 coupling matrix: box = 64 columns (128 bytes, 128-byte swizzle) x 128 rows
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_j_tensor_map(CUtensorMap* tmap, const void* J, int N) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return TSU_ERR_UNSUPPORTED;
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)N};
+  const cuuint64_t strides[1] = {(cuuint64_t)N * 2};
+  const cuuint32_t box[2] = {64, (cuuint32_t)kPanel};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(J), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? TSU_OK : TSU_ERR_UNSUPPORTED;
+}
+
 static int launch_tc(const TcParams& P, cudaStream_t st) {
-  const size_t smem = sizeof(TcSmem);
+  const size_t smem = sizeof(TcSmem) + 1024;  // slack: the dynamic shared memory base is only guaranteed 16-byte aligned
+  CUtensorMap tmap;
+  int rc = make_j_tensor_map(&tmap, P.J, P.N);
+  if (rc != TSU_OK) return rc;
   cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  dense_tc_kernel<<<(P.n_chains + kChains - 1) / kChains, kThreads, smem, st>>>(P);
+  dense_tc_kernel<<<(P.n_chains + kChains - 1) / kChains, kThreads, smem, st>>>(P, tmap);
   e = cudaGetLastError();
   return e == cudaSuccess ? TSU_OK : (int)e;
 }
