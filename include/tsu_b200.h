@@ -176,7 +176,9 @@ int tsu_dense_init_random(uint8_t* d_state, int n_chains, int N, uint64_t seed, 
  *   d_bias: [N] float32 or NULL; d_state: [n_chains][N] uint8 bits in place; N % 128 == 0, N <= 4096.
  *   Uniform of (site, chain, sweep): 24 bits of word (site & 3) of Philox(counter = (site >> 2,
  *   chain0 + chain, sweep0 + sweep, 'DENT')), compared in fp32 with sigmoid(h/T) (clamped at |x| > 20).
- *   d_fields_or_null: [n_chains][N] float32, receives the GEMM fields of the LAST sweep (diagnostics). */
+ *   d_fields_or_null: [n_chains][N] float32, diagnostics: the field of every site as the kernel compares it on
+ *   its last visit (the local field minus J[i][i'] for the earlier sites i' of the same 32-site block that were 1
+ *   before the visit; that part is folded into the acceptance threshold). */
 int tsu_dense_gibbs_tc_run(const void* d_J_bf16, const float* d_bias, uint8_t* d_state, int n_chains,
                            int N, double T, const double* d_T_chain, int n_sweeps, uint64_t seed,
                            uint32_t sweep0, uint32_t chain0, float* d_fields_or_null, uintptr_t stream);

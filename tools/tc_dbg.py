@@ -11,4 +11,4 @@ for it in range(2):
     a.record(); _lib.call("tsu_dense_gibbs_tc_run", _lib.ptr(J), None, _lib.ptr(st), C, N, 1.0, None, 4, 3, 0, 0, None, _lib.current_stream()); b.record()
     torch.cuda.synchronize()
 ms = a.elapsed_time(b) / 4
-print(f"TSU_TC_DEBUG={os.environ.get('TSU_TC_DEBUG','0')}: sweep {ms:.3f} ms = {ms*1e-3*1.965e9/4096:.0f} clk/chunk = {ms*1e-3*1.965e9/128:.0f} clk/block")
+print(f"TSU_TC_DEBUG={os.environ.get('TSU_TC_DEBUG','0')}: sweep {ms:.3f} ms = {ms*1e-3*1.965e9/4096:.0f} clk per N=32 chunk-equivalent = {ms*1e-3*1.965e9/1024:.0f} clk per panel-chunk")

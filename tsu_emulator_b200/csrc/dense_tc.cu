@@ -222,7 +222,8 @@ struct TcParams {
 constexpr int kProducers = 128 * kGroups;           // warps 0-7: 4 warps (128 chains) per group
 constexpr int kEpilogue0 = kProducers / 32;         // warps 8-11: epilogue (thread = chain = TMEM lane)
 constexpr int kIssuer0 = kEpilogue0 + 4;            // warp 12: main GEMM issuer, warp 13: in-panel correction issuer
-constexpr int kThreads = 32 * (kIssuer0 + 2);       // 448
+constexpr int kThresh0 = kIssuer0 + 2;              // warps 14-15: acceptance thresholds (Philox + logit), two chains per thread
+constexpr int kThreads = 32 * (kThresh0 + 2);       // 512
 
 // position of site i (0-31 of a block) inside a state word: even sites in the low half, odd sites in the high
 // half, so that (word >> j) & 0x00010001 is the pair (2j, 2j+1)
@@ -235,22 +236,32 @@ struct __align__(1024) JTile {
   unsigned char bytes[kTileBytes];
 };
 
-// shared memory carve-up (~197 KB; the J tiles need 1024-byte alignment for the swizzle)
+// shared memory carve-up (~213 KB; the J tiles need 1024-byte alignment for the swizzle)
 struct TcSmem {
   uint32_t sbits[4096 / 32][kChains];        // chain states, word-major: sbits[w][chain], bit order = site_bit()
   JTile b[kStages];                          // J[panel rows, chunk columns]
   JTile jdiag;                               // J[panel rows, panel columns]: operand of the in-panel corrections
   __align__(16) float jblk[kBlk][kBlk + 4];  // J[blk, blk] as fp32, transposed: jblk[i][i'] = J[i0+i'][i0+i]
+  float thr[kBlk][kChains];                  // acceptance thresholds T * logit(u) of one block, thr[site][chain]
   __align__(8) uint64_t full[kStages];       // producers -> issuer: A slot written (one arrival per warp) + J tile landed (TMA bytes)
   __align__(8) uint64_t empty[kStages];      // issuer -> producers: the MMAs reading the stage are done        (commit)
   __align__(8) uint64_t acc_full[2];         // issuer -> epilogue: main GEMM of the panel complete             (commit)
   __align__(8) uint64_t acc_free[2];         // epilogue -> issuer: accumulator buffer read out     (one arrival per warp)
   __align__(8) uint64_t panel_done[4];       // epilogue -> producers: bits of panel gp written (ring, one arrival per warp)
   __align__(8) uint64_t delta_ready;         // epilogue -> correction issuer: flips of a block are in TMEM (per warp)
+  __align__(8) uint64_t thr_full;            // threshold warps -> epilogue: thresholds of the next block written (per warp)
+  __align__(8) uint64_t thr_free;            // epilogue -> threshold warps: thresholds are in registers       (per warp)
   __align__(8) uint64_t jdiag_full;          // TMA -> correction issuer: jdiag of the panel landed
   __align__(8) uint64_t corr_done;           // correction issuer -> epilogue: the rest of the panel is corrected (commit)
   uint32_t tmem_base;
 };
+
+// log2 without the denormal pre-scaling of __log2f (the arguments are 0 or >= 2^-24)
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -303,6 +314,8 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
     mbar_init(&sm.delta_ready, 4);
     mbar_init(&sm.corr_done, 1);
     mbar_init(&sm.jdiag_full, 1);
+    mbar_init(&sm.thr_full, 2);
+    mbar_init(&sm.thr_free, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kIssuer0) {
@@ -338,9 +351,13 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
           }
           TC_T0();
           if (row == 0) {  // J[panel p rows, chunk kc columns]: two 16 KB boxes, bytes counted on the stage's full barrier
-            mbar_arrive_expect_tx(&sm.full[s], kTileBytes);
-            tma_load_2d(sm.b[s].bytes, &tmap, kc * kKC, p * kPanel, &sm.full[s]);
-            tma_load_2d(sm.b[s].bytes + kHalfBytes, &tmap, kc * kKC + 64, p * kPanel, &sm.full[s]);
+            if (P.dbg & 4) {
+              mbar_arrive(&sm.full[s]);
+            } else {
+              mbar_arrive_expect_tx(&sm.full[s], kTileBytes);
+              tma_load_2d(sm.b[s].bytes, &tmap, kc * kKC, p * kPanel, &sm.full[s]);
+              tma_load_2d(sm.b[s].bytes + kHalfBytes, &tmap, kc * kKC + 64, p * kPanel, &sm.full[s]);
+            }
           }
           if (warp == 0) TC_NEXT(16);
           const int need = (cc == n_panels - 1) ? gp : gp - 1;
@@ -445,15 +462,58 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
         }
       }
     }
+  } else if (warp >= kThresh0) {
+    // ===================== threshold warps: T * logit(u) for every (chain, site), one block ahead ===========
+    //   u < sigmoid(h / T)  <=>  h > T * logit(u)          (gibbs.py:61-77,126; strict <)
+    // and the clamp of gibbs.py:65-70 (|h/T| > 20 -> p = 1 / 0) is the clamp of the threshold to +-20 T.
+    // This takes Philox, exp and the division off the epilogue's site-to-site dependency chain.
+    if (!P.gemm_only) {
+      const int t = tid - 32 * kThresh0;  // 0..63: chains t and t + 64 of the tile
+      float Tc[2];
+      uint32_t cg[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int chain = blockIdx.x * kChains + t + 64 * c;
+        Tc[c] = P.T_chain ? (float)P.T_chain[chain < P.n_chains ? chain : 0] : P.T;
+        cg[c] = P.chain0 + (uint32_t)chain;
+      }
+      const int total_blk = total_panels * 4;
+      for (int gblk = 0; gblk < total_blk; ++gblk) {
+        const int gp = gblk >> 2, p = gp % n_panels, sweep = gp / n_panels;
+        const int i0 = (4 * p + (gblk & 3)) * kBlk;
+        // compute into registers first: this overlaps with the epilogue still using the previous block's thresholds
+        float v[2][kBlk];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int i = 0; i < kBlk; i += 4) {
+            const tsu_u32x4 o = tsu_philox4x32_10((uint32_t)((i0 + i) >> 2), cg[c], P.sweep0 + (uint32_t)sweep,
+                                                  TSU_STREAM_DENSE_TC, P.k0, P.k1);
+            const uint32_t r4[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float u = (float)(r4[k] >> 8) * (1.0f / 16777216.0f);  // 24-bit uniform, exact in fp32
+              const float lg = (lg2_ftz(u) - lg2_ftz(1.0f - u)) * 0.69314718056f;  // u = 0 -> -inf -> clamped
+              v[c][i + k] = fminf(fmaxf(lg, -20.0f), 20.0f) * Tc[c];
+            }
+          }
+        }
+        if (gblk > 0) mbar_wait(&sm.thr_free, (uint32_t)((gblk - 1) & 1));  // the previous block's thresholds are in registers
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int i = 0; i < kBlk; ++i) sm.thr[i][t + 64 * c] = v[c][i];
+        }
+        warp_arrive(&sm.thr_full);
+      }
+    }
   } else {
     // ===================== epilogue: fields out of TMEM, sequential update block by block ================
     const int row = tid - kProducers;                    // TMEM lane = chain within the tile
     const int chain = blockIdx.x * kChains + row;
     const bool chain_ok = chain < P.n_chains;
     const uint32_t tmem_lane = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
-    const float T = P.T_chain ? (float)P.T_chain[chain_ok ? chain : 0] : P.T;
-    const uint32_t chain_g = P.chain0 + (uint32_t)chain;
-    uint32_t accf_phase = 0, corr_phase = 0;
+    uint32_t accf_phase = 0, corr_phase = 0, thr_phase = 0;
     // diagonal block J[blk, blk]: 8 bf16 per thread (row i0 + row/4, columns i0 + 8 (row%4) ..), fetched one
     // block ahead so that the load latency hides behind the previous block's update
     auto load_diag = [&](int blk) {
@@ -492,25 +552,24 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
         jd = load_diag((blk + 1) % n_blocks);
         named_bar_sync(1, kChains);
         TC_B(25);
-        // Acceptance thresholds of the block, computed while the tensor core is still busy:
-        //   u < sigmoid(h / T)  <=>  h > T * logit(u)          (gibbs.py:61-77,126; strict <)
-        // and the clamp of gibbs.py:65-70 (|h/T| > 20 -> p = 1 / 0) is the clamp of the threshold to +-20 T.
-        // This takes exp, the division and the Philox call off the site-to-site dependency chain: per site the
-        // chain is compare -> select -> fma.
+        // Thresholds of the block (threshold warps) -> registers, then everything that does not depend on the fields:
+        // the in-block correction is split as  J (new - old) = J new - J old,  and the "- J old" part of every
+        // earlier site of the block is moved to the other side of the comparison, thr'[i'] = thr[i'] + sum_{i<i'}
+        // J[i',i] old_i.  The site-to-site dependency chain is then: compare -> 0/1 -> fma.
         float thr[kBlk];
+        const uint32_t w_old = sm.sbits[blk][row];
         if (!P.gemm_only) {
+          mbar_wait(&sm.thr_full, thr_phase);
+          thr_phase ^= 1u;
 #pragma unroll
-          for (int i = 0; i < kBlk; i += 4) {
-            const tsu_u32x4 o = tsu_philox4x32_10((uint32_t)((i0 + i) >> 2), chain_g, P.sweep0 + (uint32_t)sweep,
-                                                  TSU_STREAM_DENSE_TC, P.k0, P.k1);
-            const uint32_t r4[4] = {o.x, o.y, o.z, o.w};
+          for (int i = 0; i < kBlk; ++i) thr[i] = sm.thr[i][row];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float u = (float)(r4[k] >> 8) * (1.0f / 16777216.0f);  // 24-bit uniform, exact in fp32
-              const float lg = (__log2f(u) - __log2f(1.0f - u)) * 0.69314718056f;
-              thr[i + k] = fminf(fmaxf(lg, -20.0f), 20.0f) * T;
-            }
+          for (int i = 0; i < kBlk; ++i) {
+            const float old_i = ((w_old >> site_bit(i)) & 1u) ? 1.0f : 0.0f;
+#pragma unroll
+            for (int ip = i + 1; ip < kBlk; ++ip) thr[ip] = fmaf(sm.jblk[i][ip], old_i, thr[ip]);
           }
+          warp_arrive(&sm.thr_free);
         }
         TC_B(26);
         {
@@ -545,19 +604,16 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
         } else {
           // sequential heat-bath update of the 32 sites of this block for this thread's chain (gibbs.py:153-160)
           static_assert(kBlk == 32, "one state word per block");
-          const uint32_t w_old = sm.sbits[blk][row];
           uint32_t w_new = 0;
 #pragma unroll
           for (int i = 0; i < kBlk; ++i) {
-            if (P.fields_out && chain_ok) P.fields_out[(size_t)chain * N + i0 + i] = h[i];  // field at visit time
-            const float d_up = ((w_old >> site_bit(i)) & 1u) ? 0.0f : 1.0f;   // new - old if the site comes out 1 ...
-            const float d_dn = d_up - 1.0f;                                    // ... or 0 (both known before the chain)
+            if (P.fields_out && chain_ok) P.fields_out[(size_t)chain * N + i0 + i] = h[i];  // as compared (diagnostics)
             const bool up = h[i] > thr[i];
-            const float delta = up ? d_up : d_dn;
+            const float s_new = up ? 1.0f : 0.0f;
             w_new |= up ? (1u << site_bit(i)) : 0u;
             // not yet visited sites of the block see the new value (rank-1 correction, branch free)
 #pragma unroll
-            for (int ip = i + 1; ip < kBlk; ++ip) h[ip] = fmaf(sm.jblk[i][ip], delta, h[ip]);
+            for (int ip = i + 1; ip < kBlk; ++ip) h[ip] = fmaf(sm.jblk[i][ip], s_new, h[ip]);
           }
           sm.sbits[blk][row] = w_new;
           TC_B(29);
