@@ -34,19 +34,23 @@ if "--cpu" in sys.argv:
     out.append({"config": "C1-cpu", "workload": "literal port of tsu/gibbs.py:128-162, IsingGrid((50,50)) dense J, 1 core, 100 sweeps x10",
                 "wall_s_1000_sweeps": dt, "spin_updates_per_s": 2.5e6 / dt})
 # ---- C3: dense SK N=4096, 2048 chains, 10 sweeps on the tensor cores ---------------------------------------
-N, C, SW = 4096, 2048, 10
+N, SW = 4096, 10
 rng = np.random.default_rng(7)
 J = rng.normal(size=(N, N)) / np.sqrt(N); J = (J + J.T) / np.sqrt(2); np.fill_diagonal(J, 0)
 Jd = torch.from_numpy(J).cuda().to(torch.bfloat16).contiguous()
-st = (torch.rand(C, N, device="cuda") < 0.5).to(torch.uint8)
-_lib.call("tsu_dense_gibbs_tc_run", _lib.ptr(Jd), None, _lib.ptr(st), C, N, 1.0, None, 1, 3, 0, 0, None, _lib.current_stream())
-a, b = ev(); a.record()
-_lib.call("tsu_dense_gibbs_tc_run", _lib.ptr(Jd), None, _lib.ptr(st), C, N, 1.0, None, SW, 3, 1, 0, None, _lib.current_stream())
-b.record(); torch.cuda.synchronize(); ms = a.elapsed_time(b)
-upd = C * N * SW
-out.append({"config": "C3", "workload": "GibbsSampler dense SK J (bf16) N=4096, 2048 chains, 10 sequential sweeps, tcgen05",
-            "ms": ms, "spin_updates_per_s": upd / ms * 1e3, "tflops": upd * 2 * N / ms * 1e3 / 1e12,
-            "tensor_roofline_frac_of_1399.3": upd * 2 * N / ms * 1e3 / 1399.3e12, "ctas": C // 128})
+n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+for C, tag in ((2048, "C3"), (128 * n_sm, "C3-full-wave (same N, one 128-chain tile per SM)")):
+    st = (torch.rand(C, N, device="cuda") < 0.5).to(torch.uint8)
+    _lib.call("tsu_dense_gibbs_tc_run", _lib.ptr(Jd), None, _lib.ptr(st), C, N, 1.0, None, 1, 3, 0, 0, None, _lib.current_stream())
+    a, b = ev(); a.record()
+    _lib.call("tsu_dense_gibbs_tc_run", _lib.ptr(Jd), None, _lib.ptr(st), C, N, 1.0, None, SW, 3, 1, 0, None, _lib.current_stream())
+    b.record(); torch.cuda.synchronize(); ms = a.elapsed_time(b)
+    upd = C * N * SW
+    m = 64 if (C + 127) // 128 < n_sm else 128      # chains per CTA, as chosen in csrc/dense_tc.cu
+    out.append({"config": tag, "workload": f"GibbsSampler dense SK J (bf16) N={N}, {C} chains, {SW} sequential sweeps, tcgen05",
+                "ms": ms, "spin_updates_per_s": upd / ms * 1e3, "tflops": upd * 2 * N / ms * 1e3 / 1e12,
+                "tensor_roofline_frac_of_1399.3": upd * 2 * N / ms * 1e3 / 1399.3e12, "chains_per_cta": m, "ctas": (C + m - 1) // m})
+    del st
 # ---- C4 (one GPU): 131072 x 131072 single lattice --------------------------------------------------------
 rows = cols = 131072
 fac = lambda lr, r0: Ising2DEngine(lr, cols, temperature=2.269, periodic=True, seed=1, row0=r0, global_rows=rows).init_random()

@@ -20,7 +20,7 @@ names = {0: "issuer wait full (per chunk)", 2: "issuer wait acc_free", 3: "P0 wa
          19: "P0w0 cp.async.wait_group 0", 20: "P0w0 fence+syncwarp+arrive", 21: "issuer membar+fence", 22: "issuer mma+commit+syncwarp",
          23: "corr issuer wait delta_ready", 24: "corr issuer fence+mma+commit", 11: "EPI wait acc_full (per panel)",
          13: "EPI wait corr_done (3 per panel)", 12: "EPI ld+update+delta (4 per panel)",
-         25: "EPI jblk staging + 2 named barriers", 26: "EPI thr wait+load+prepass", 27: "EPI waits", 28: "EPI ldtm", 29: "EPI scale+chain", 30: "EPI delta sttm+arrive"}
+         25: "EPI (unused)", 26: "EPI thr wait+load(+prepass M128)", 27: "EPI waits", 28: "EPI ldtm", 29: "EPI scale+chain", 30: "EPI delta sttm+arrive"}
 nchunks = 2 * 32 * 32
 print(f"2 sweeps: {ms:.2f} ms = {total_clk:.3e} clk; chunks per CTA = {nchunks}; {total_clk/nchunks:.0f} clk/chunk")
 for i, n in sorted(names.items()):

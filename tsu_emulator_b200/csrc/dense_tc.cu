@@ -34,7 +34,7 @@
 
 namespace {
 
-constexpr int kChains = 128;  // chains per CTA = UMMA M = TMEM lanes
+constexpr int kChains = 128;  // TMEM lanes = threads per role group; chains per CTA = UMMA M = kM (128 or 64, template parameter)
 constexpr int kBlk = 32;      // sites per block (sequential update unit of the epilogue)
 constexpr int kKC = 128;      // K-chunk (sites) per pipeline stage
 constexpr int kPanel = 128;   // sites per panel = UMMA N of the main GEMM; a panel is also exactly one K-chunk
@@ -241,7 +241,7 @@ struct TcSmem {
   uint32_t sbits[4096 / 32][kChains];        // chain states, word-major: sbits[w][chain], bit order = site_bit()
   JTile b[kStages];                          // J[panel rows, chunk columns]
   JTile jdiag;                               // J[panel rows, panel columns]: operand of the in-panel corrections
-  __align__(16) float jblk[kBlk][kBlk + 4];  // J[blk, blk] as fp32, transposed: jblk[i][i'] = J[i0+i'][i0+i]
+  __align__(16) float jblk[2][kBlk][kBlk + 4];  // J[blk, blk] as fp32, transposed: jblk[.][i][i'] = J[i0+i'][i0+i]; block g in buffer g & 1
   float thr[kBlk][kChains];                  // acceptance thresholds T * logit(u) of one block, thr[site][chain]
   __align__(8) uint64_t full[kStages];       // producers -> issuer: A slot written (one arrival per warp) + J tile landed (TMA bytes)
   __align__(8) uint64_t empty[kStages];      // issuer -> producers: the MMAs reading the stage are done        (commit)
@@ -250,6 +250,7 @@ struct TcSmem {
   __align__(8) uint64_t panel_done[4];       // epilogue -> producers: bits of panel gp written (ring, one arrival per warp)
   __align__(8) uint64_t delta_ready;         // epilogue -> correction issuer: flips of a block are in TMEM (per warp)
   __align__(8) uint64_t thr_full;            // threshold warps -> epilogue: thresholds of the next block written (per warp)
+  __align__(8) uint64_t jblk_ready;          // epilogue -> threshold warps: jblk of the next block is staged     (per warp)
   __align__(8) uint64_t thr_free;            // epilogue -> threshold warps: thresholds are in registers       (per warp)
   __align__(8) uint64_t jdiag_full;          // TMA -> correction issuer: jdiag of the panel landed
   __align__(8) uint64_t corr_done;           // correction issuer -> epilogue: the rest of the panel is corrected (commit)
@@ -275,6 +276,19 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
 
+// chain (row of the M x N tile) served by thread t (0..127) of a role group.  UMMA M = 128: TMEM lane = row.
+// UMMA M = 64: row m lives in lane 32 (m / 16) + m % 16, i.e. the lower half of every 32-lane quarter; the
+// upper-half threads shadow their lower twins (same loads, same arithmetic, no stores).
+template <int kM>
+__device__ __forceinline__ int chain_row(int t) {
+  return kM == 128 ? t : 16 * (t >> 5) + (t & 15);
+}
+template <int kM>
+__device__ __forceinline__ bool chain_lane_active(int t) {
+  return kM == 128 || (t & 31) < 16;
+}
+
+template <int kM>
 __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // round the base up to 1024 bytes in the SHARED address space (keeps the compiler on LDS/STS)
@@ -282,11 +296,12 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
   const int tid = threadIdx.x, warp = tid >> 5;
   const int N = P.N;
   const int n_panels = N / kPanel;  // = number of K-chunks
+  constexpr bool kPrepassAhead = (kM == 64);  // who folds the old spins into the thresholds (see the epilogue)
   const int total_panels = n_panels * P.n_sweeps;
 
   // ---- one-time setup -------------------------------------------------------------------------
-  if (tid < kChains) {  // pack this chain's bits
-    const int chain = blockIdx.x * kChains + tid;
+  if (tid < kM) {  // pack this chain's bits
+    const int chain = blockIdx.x * kM + tid;
     for (int w = 0; w < N / 32; ++w) {
       uint32_t x = 0;
       if (chain < P.n_chains) {
@@ -316,6 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
     mbar_init(&sm.jdiag_full, 1);
     mbar_init(&sm.thr_full, 2);
     mbar_init(&sm.thr_free, 4);
+    mbar_init(&sm.jblk_ready, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kIssuer0) {
@@ -331,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
     // ===================== producers: stream J tiles, expand spins to bf16 A tiles ======================
     // group q = warp / 4 handles the chunks g = q, q + kGroups, ... of the global sequence (panel-major);
     // thread = chain (TMEM lane)
-    const int q = warp >> 2, row = tid & (kChains - 1);
+    const int q = warp >> 2, row = chain_row<kM>(tid & (kChains - 1));
     int done_seen = 0;  // number of panel_done phases consumed
     long long g = 0;
     int s = 0;          // stage of chunk g
@@ -350,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
             if ((warp & 3) == 0) TC_ACC(3 + 4 * q);
           }
           TC_T0();
-          if (row == 0) {  // J[panel p rows, chunk kc columns]: two 16 KB boxes, bytes counted on the stage's full barrier
+          if ((tid & (kChains - 1)) == 0) {  // J[panel p rows, chunk kc columns]: two 16 KB boxes, bytes counted on the stage's full barrier
             if (P.dbg & 4) {
               mbar_arrive(&sm.full[s]);
             } else {
@@ -394,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
     // ===================== main GEMM issuer: one elected lane feeds the tensor core ======================
     // The whole warp runs the loop (uniform control flow keeps counters and descriptors in uniform registers);
     // only the tcgen05.mma / commit instructions are issued by the elected lane.
-    const uint32_t idesc = umma_idesc(kChains, kPanel);
+    const uint32_t idesc = umma_idesc(kM, kPanel);
     const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sm.b[0].bytes));
     constexpr uint32_t kSlotUnits = (uint32_t)(kTileBytes >> 4);  // 16-byte units per ring slot
     uint32_t full_phase = 0, free_phase = 0;
@@ -449,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
           tc_fence_after();
           if (elect_one()) {
             const int n_cols = kPanel - kBlk * (b + 1);               // columns (sites) of the blocks still to come
-            const uint32_t idesc = umma_idesc(kChains, n_cols);
+            const uint32_t idesc = umma_idesc(kM, n_cols);
             // rows (sites) 32 (b+1) .. 127 of jdiag (8-row groups of 1024 bytes), K = sites 32 b .. 32 b + 31 of the panel
             const uint64_t bd = jd_desc0 + (uint64_t)(((uint32_t)(b >> 1) * kHalfBytes + (uint32_t)(4 * (b + 1)) * 1024u + (uint32_t)(b & 1) * 64u) >> 4);
 #pragma unroll
@@ -468,12 +484,13 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
     // and the clamp of gibbs.py:65-70 (|h/T| > 20 -> p = 1 / 0) is the clamp of the threshold to +-20 T.
     // This takes Philox, exp and the division off the epilogue's site-to-site dependency chain.
     if (!P.gemm_only) {
-      const int t = tid - 32 * kThresh0;  // 0..63: chains t and t + 64 of the tile
-      float Tc[2];
-      uint32_t cg[2];
+      const int t = tid - 32 * kThresh0;  // 0..63: chains t and (M = 128) t + 64 of the tile
+      constexpr int kPer = kM / 64;
+      float Tc[kPer];
+      uint32_t cg[kPer];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int chain = blockIdx.x * kChains + t + 64 * c;
+      for (int c = 0; c < kPer; ++c) {
+        const int chain = blockIdx.x * kM + t + 64 * c;
         Tc[c] = P.T_chain ? (float)P.T_chain[chain < P.n_chains ? chain : 0] : P.T;
         cg[c] = P.chain0 + (uint32_t)chain;
       }
@@ -482,11 +499,13 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
         const int gp = gblk >> 2, p = gp % n_panels, sweep = gp / n_panels;
         const int i0 = (4 * p + (gblk & 3)) * kBlk;
         // compute into registers first: this overlaps with the epilogue still using the previous block's thresholds
-        float v[2][kBlk];
+        float v[kPer][kBlk];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < kPer; ++c) {
 #pragma unroll
-          for (int i = 0; i < kBlk; i += 4) {
+          for (int i = 0; i < kBlk && (P.dbg & 16); ++i) v[c][i] = 0.0f;
+#pragma unroll
+          for (int i = 0; i < kBlk && !(P.dbg & 16); i += 4) {
             const tsu_u32x4 o = tsu_philox4x32_10((uint32_t)((i0 + i) >> 2), cg[c], P.sweep0 + (uint32_t)sweep,
                                                   TSU_STREAM_DENSE_TC, P.k0, P.k1);
             const uint32_t r4[4] = {o.x, o.y, o.z, o.w};
@@ -498,9 +517,20 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
             }
           }
         }
+        if (kPrepassAhead && !(P.dbg & 32)) {
+          // the "- J old" half of the in-block correction moves to the threshold side (see the epilogue)
+          mbar_wait(&sm.jblk_ready, (uint32_t)(gblk & 1));
+          const uint32_t w_old = sm.sbits[4 * p + (gblk & 3)][t];
+#pragma unroll
+          for (int i = 0; i < kBlk; ++i) {
+            const float old_i = ((w_old >> site_bit(i)) & 1u) ? 1.0f : 0.0f;
+#pragma unroll
+            for (int ip = i + 1; ip < kBlk; ++ip) v[0][ip] = fmaf(sm.jblk[gblk & 1][i][ip], old_i, v[0][ip]);
+          }
+        }
         if (gblk > 0) mbar_wait(&sm.thr_free, (uint32_t)((gblk - 1) & 1));  // the previous block's thresholds are in registers
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < kPer; ++c) {
 #pragma unroll
           for (int i = 0; i < kBlk; ++i) sm.thr[i][t + 64 * c] = v[c][i];
         }
@@ -509,53 +539,55 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
     }
   } else {
     // ===================== epilogue: fields out of TMEM, sequential update block by block ================
-    const int row = tid - kProducers;                    // TMEM lane = chain within the tile
-    const int chain = blockIdx.x * kChains + row;
-    const bool chain_ok = chain < P.n_chains;
+    const int t128 = tid - kProducers;                   // thread of the role group = TMEM lane
+    const int row = chain_row<kM>(t128);                 // chain within the tile
+    const int chain = blockIdx.x * kM + row;
+    const bool chain_ok = chain < P.n_chains && chain_lane_active<kM>(t128);
     const uint32_t tmem_lane = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t accf_phase = 0, corr_phase = 0, thr_phase = 0;
-    // diagonal block J[blk, blk]: 8 bf16 per thread (row i0 + row/4, columns i0 + 8 (row%4) ..), fetched one
+    // diagonal block J[blk, blk]: 8 bf16 per thread (row i0 + t128/4, columns i0 + 8 (t128%4) ..), fetched one
     // block ahead so that the load latency hides behind the previous block's update
     auto load_diag = [&](int blk) {
       const int i0 = blk * kBlk;
-      return __ldg(reinterpret_cast<const uint4*>(P.J + (size_t)(i0 + (row >> 2)) * N + i0 + 8 * (row & 3)));
+      return __ldg(reinterpret_cast<const uint4*>(P.J + (size_t)(i0 + (t128 >> 2)) * N + i0 + 8 * (t128 & 3)));
     };
-    uint4 jd = load_diag(0);
     const int n_blocks = N / kBlk;
+    auto stage_jblk = [&](int buf2, const uint4& v) {  // diagonal block as fp32, transposed: jblk[i][i'] = J[i0 + i', i0 + i]
+      const uint32_t jw[4] = {v.x, v.y, v.z, v.w};
+      const int r = t128 >> 2, c0 = 8 * (t128 & 3);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        sm.jblk[buf2][c0 + 2 * e][r] = __uint_as_float(jw[e] << 16);  // bf16 -> fp32 is a 16-bit shift
+        sm.jblk[buf2][c0 + 2 * e + 1][r] = __uint_as_float(jw[e] & 0xffff0000u);
+      }
+    };
+    stage_jblk(0, load_diag(0));
+    uint4 jd = load_diag(1 % n_blocks);  // always one block ahead of the staged one
+    named_bar_sync(1, kChains);
+    if (kPrepassAhead && !P.gemm_only) warp_arrive(&sm.jblk_ready);
+    int gblk = 0;
     for (int gp = 0; gp < total_panels; ++gp) {
-      const int p = gp % n_panels, sweep = gp / n_panels, buf = gp & 1;
+      const int p = gp % n_panels, buf = gp & 1;
       // J[panel, panel] for this panel's corrections; the previous panel's corrections are all complete
-      if (!P.gemm_only && row == 0) {
+      if (!P.gemm_only && t128 == 0) {
         mbar_arrive_expect_tx(&sm.jdiag_full, kTileBytes);
         tma_load_2d(sm.jdiag.bytes, &tmap, p * kPanel, p * kPanel, &sm.jdiag_full);
         tma_load_2d(sm.jdiag.bytes + kHalfBytes, &tmap, p * kPanel + 64, p * kPanel, &sm.jdiag_full);
       }
-      for (int b = 0; b < 4; ++b) {
-        const int blk = 4 * p + b, i0 = blk * kBlk;
+      for (int b = 0; b < 4; ++b, ++gblk) {
+        const int blk = 4 * p + b, i0 = blk * kBlk, jb = gblk & 1;
 #ifdef TSU_TC_TIMING
         long long tb__ = clock64();
 #define TC_B(i) do { const long long t1__ = clock64(); if (blockIdx.x == 0 && tid == kProducers) atomicAdd(&g_tc_timing[i], (unsigned long long)(t1__ - tb__)); tb__ = t1__; } while (0)
 #else
 #define TC_B(i) do {} while (0)
 #endif
-        // diagonal block as fp32, transposed: jblk[i][i'] = J[i0 + i', i0 + i]
-        named_bar_sync(1, kChains);  // everybody is done with the previous block's jblk
-        {
-          const uint32_t jw[4] = {jd.x, jd.y, jd.z, jd.w};
-          const int r = row >> 2, c0 = 8 * (row & 3);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            sm.jblk[c0 + 2 * e][r] = __uint_as_float(jw[e] << 16);  // bf16 -> fp32 is a 16-bit shift
-            sm.jblk[c0 + 2 * e + 1][r] = __uint_as_float(jw[e] & 0xffff0000u);
-          }
-        }
-        jd = load_diag((blk + 1) % n_blocks);
-        named_bar_sync(1, kChains);
-        TC_B(25);
-        // Thresholds of the block (threshold warps) -> registers, then everything that does not depend on the fields:
-        // the in-block correction is split as  J (new - old) = J new - J old,  and the "- J old" part of every
-        // earlier site of the block is moved to the other side of the comparison, thr'[i'] = thr[i'] + sum_{i<i'}
-        // J[i',i] old_i.  The site-to-site dependency chain is then: compare -> 0/1 -> fma.
+        // Thresholds of the block (threshold warps) -> registers.  The in-block correction is split as
+        // J (new - old) = J new - J old, and the "- J old" part of every earlier site of the block is moved to the
+        // other side of the comparison, thr'[i'] = thr[i'] + sum_{i<i'} J[i',i] old_i: nothing of it depends on the
+        // fields, so it is done ahead - by the threshold warps (M = 64, one chain per thread there) or here while
+        // the correction MMA of the previous block is in flight (M = 128).  The site-to-site dependency chain is
+        // then: compare -> 0/1 -> fma.
         float thr[kBlk];
         const uint32_t w_old = sm.sbits[blk][row];
         if (!P.gemm_only) {
@@ -563,11 +595,13 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
           thr_phase ^= 1u;
 #pragma unroll
           for (int i = 0; i < kBlk; ++i) thr[i] = sm.thr[i][row];
+          if (!kPrepassAhead) {
 #pragma unroll
-          for (int i = 0; i < kBlk; ++i) {
-            const float old_i = ((w_old >> site_bit(i)) & 1u) ? 1.0f : 0.0f;
+            for (int i = 0; i < kBlk; ++i) {
+              const float old_i = ((w_old >> site_bit(i)) & 1u) ? 1.0f : 0.0f;
 #pragma unroll
-            for (int ip = i + 1; ip < kBlk; ++ip) thr[ip] = fmaf(sm.jblk[i][ip], old_i, thr[ip]);
+              for (int ip = i + 1; ip < kBlk; ++ip) thr[ip] = fmaf(sm.jblk[jb][i][ip], old_i, thr[ip]);
+            }
           }
           warp_arrive(&sm.thr_free);
         }
@@ -575,7 +609,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
         {
           TC_T0();
           if (b == 0) {
-            mbar_wait_backoff(&sm.acc_full[buf], (accf_phase >> buf) & 1u);  // main GEMM of the panel
+            mbar_wait(&sm.acc_full[buf], (accf_phase >> buf) & 1u);  // main GEMM of the panel
             accf_phase ^= 1u << buf;
             if (warp == kEpilogue0) TC_ACC(11);
           } else if (!P.gemm_only) {
@@ -594,6 +628,9 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
           tc_fence_before();
           warp_arrive(&sm.acc_free[buf]);  // the tensor core may overwrite this buffer (panel gp + 2)
         }
+        // the next block's diagonal couplings go to the other jblk buffer (its previous user, block gblk - 1, is done)
+        stage_jblk(jb ^ 1, jd);
+        jd = load_diag((blk + 2) % n_blocks);
 #pragma unroll
         for (int i = 0; i < kBlk; ++i) h[i] = fmaf(h[i], 0.5f, P.bias ? __ldg(P.bias + i0 + i) : 0.0f);  // spins were 0 / 2
         if (P.gemm_only) {
@@ -613,9 +650,9 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
             w_new |= up ? (1u << site_bit(i)) : 0u;
             // not yet visited sites of the block see the new value (rank-1 correction, branch free)
 #pragma unroll
-            for (int ip = i + 1; ip < kBlk; ++ip) h[ip] = fmaf(sm.jblk[i][ip], s_new, h[ip]);
+            for (int ip = i + 1; ip < kBlk && !(P.dbg & 8); ++ip) h[ip] = fmaf(sm.jblk[jb][i][ip], s_new, h[ip]);
           }
-          sm.sbits[blk][row] = w_new;
+          if (chain_lane_active<kM>(t128)) sm.sbits[blk][row] = w_new;
           TC_B(29);
           if (b < 3) {
             // flips of the block as a bf16 operand in the accumulator's units (spins are 0 / 2): +2 = 0x4000, -2 = 0xC000
@@ -631,9 +668,11 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
             TC_B(30);
           }
         }
+        if (b == 3) warp_arrive(&sm.panel_done[gp & 3]);  // release: the producers may expand the chunk holding this panel
+        named_bar_sync(1, kChains);  // the next block's jblk is complete, everybody is done with this block's
+        if (kPrepassAhead && !P.gemm_only) warp_arrive(&sm.jblk_ready);
         if (warp == kEpilogue0) TC_ACC(12);
-      }
-      warp_arrive(&sm.panel_done[gp & 3]);  // release: the producers may expand the chunk holding this panel
+      }  // release: the producers may expand the chunk holding this panel
     }
     if (!P.gemm_only && chain_ok) {  // unpack the final bits of this chain
       for (int w = 0; w < N / 32; ++w) {
@@ -686,9 +725,23 @@ static int launch_tc(const TcParams& P, cudaStream_t st) {
   CUtensorMap tmap;
   int rc = make_j_tensor_map(&tmap, P.J, P.N);
   if (rc != TSU_OK) return rc;
-  cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  dense_tc_kernel<<<(P.n_chains + kChains - 1) / kChains, kThreads, smem, st>>>(P, tmap);
+  // chains per CTA: 128 fills the tensor core's M; with few chains 64 per CTA puts twice as many SMs to work (a
+  // tcgen05.mma with M = 64 takes as long as one with M = 128, so this only pays while SMs would otherwise idle)
+  int sm_count = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  int m = (P.n_chains + 127) / 128 < sm_count ? 64 : 128;
+  if (const char* env = getenv("TSU_TC_M")) m = atoi(env) == 64 ? 64 : 128;
+  cudaError_t e;
+  if (m == 64) {
+    e = cudaFuncSetAttribute(dense_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dense_tc_kernel<64><<<(P.n_chains + 63) / 64, kThreads, smem, st>>>(P, tmap);
+  } else {
+    e = cudaFuncSetAttribute(dense_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dense_tc_kernel<128><<<(P.n_chains + 127) / 128, kThreads, smem, st>>>(P, tmap);
+  }
   e = cudaGetLastError();
   return e == cudaSuccess ? TSU_OK : (int)e;
 }
