@@ -191,3 +191,35 @@ def test_tensor_core_sweeps_gaussian_couplings_mismatch_budget():
         bad += int((out[c] != want).any())
         assert e[c] == pytest.approx(D.compute_energy(out[c].astype(float), J), abs=1e-3)
     assert bad <= 3, f"{bad} of {C} chains differ from the float64 oracle"
+
+
+@pytest.mark.parametrize("tile_m", ["64", "128"])
+def test_tensor_core_multi_panel_multi_sweep_exact(tile_m, monkeypatch):
+    """three 128-site panels, two sweeps, bias and per-chain temperatures through the C-ABI, for both tile heights
+    (chains per CTA = 64 / 128): exercises the late K-chunk ordering, the in-panel correction MMAs and the ring
+    wrap-around.  Integer couplings keep bf16 / fp32 exact, so the result must equal the site-by-site oracle."""
+    import torch
+    from tsu_emulator_b200 import _lib
+    monkeypatch.setenv("TSU_TC_M", tile_m)
+    rng = np.random.default_rng(11)
+    N, C, n_sweeps, seed = 384, 70, 2, 777
+    J = rng.integers(-2, 3, (N, N)).astype(np.float64)
+    J = np.triu(J, 1); J = J + J.T
+    np.fill_diagonal(J, rng.integers(-1, 2, N))
+    b = rng.integers(-2, 3, N).astype(np.float64) * 0.25
+    T = rng.uniform(0.8, 3.0, C)
+    init = rng.integers(0, 2, (C, N)).astype(np.uint8)
+    Jd = torch.from_numpy(J).cuda().to(torch.bfloat16).contiguous()
+    bd = torch.from_numpy(b.astype(np.float32)).cuda()
+    Td = torch.from_numpy(T).cuda()
+    st = torch.from_numpy(init).cuda()
+    sweep0, chain0 = 5, 1000
+    _lib.call("tsu_dense_gibbs_tc_run", _lib.ptr(Jd), _lib.ptr(bd), _lib.ptr(st), C, N, 1.0, _lib.ptr(Td), n_sweeps, seed,
+              sweep0, chain0, None, _lib.current_stream())
+    out = st.cpu().numpy()
+    bad = 0
+    for c in range(C):
+        U = np.stack([D.philox_uniforms_tc(seed, chain0 + c, sweep0 + s, N) for s in range(n_sweeps)])
+        want = D.gibbs_sweeps(init[c].astype(int), J, b, T[c], n_sweeps, U)
+        bad += int((out[c] != want).any())
+    assert bad <= 1, f"{bad} of {C} chains differ (tile height {tile_m})"
