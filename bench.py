@@ -209,7 +209,13 @@ def run_b200_arm(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the B200 arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    json_fd = None
     if world > 1:
+        # NCCL prints its version / debug lines on fd 1 (the image sets NCCL_DEBUG=VERSION).  stdout must carry only
+        # the JSON line: park the real stdout and let everything else go to stderr until the line is written.
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_rep = args.replicas
     size = args.size
@@ -362,7 +368,12 @@ def run_b200_arm(args):
         "gpu_launches": n_launches,
         "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    if json_fd is not None:
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+        os.close(json_fd)
+    else:
+        print(json.dumps(line), flush=True)
 
 
 def main():
