@@ -192,3 +192,44 @@ def test_jit_specialised_and_prebuilt_kernels_agree(monkeypatch):
     e.init_random().sweep(3)
     want = O.checkerboard_sweeps_philox(O.init_bits(seed, 0, rows, cols), seed, 0, 0, 3, 1.0, 0.0, 0.1, True)
     assert (e.get_spins(pm1=False)[0] == want).all()
+
+
+def test_binder_cumulant_crossing_at_tc():
+    """statistical parity: the Binder cumulant U4 = 1 - <m^4> / (3 <m^2>^2) of L = 32, 64, 128 periodic
+    lattices orders by size below T_c, inverts above, and the curves cross at T_c = 2/ln(1+sqrt 2) = 2.269
+    (ising.py:312) within jackknife error bars (replicas are independent Markov chains)."""
+    import torch
+
+    temps = (2.24, 2.269, 2.30)
+    sizes = {32: (256, 4000, 60, 50), 64: (256, 30000, 60, 250), 128: (128, 120000, 50, 1000)}  # R, n_eq, n_meas, stride
+    U, err = {}, {}
+    for L, (R, n_eq, n_meas, stride) in sizes.items():
+        for T in temps:
+            eng = make_engine(L, L, n_replicas=R, temperature=T, periodic=True, seed=1000 * L + int(100 * T))
+            eng.init_random()
+            eng.sweep(n_eq)
+            m2 = torch.zeros(R, dtype=torch.float64, device="cuda")
+            m4 = torch.zeros_like(m2)
+            for _ in range(n_meas):
+                eng.sweep(stride)
+                m = (2.0 * eng.observables_tensor()[:, 0].to(torch.float64) - L * L) / (L * L)
+                m2 += m * m
+                m4 += m ** 4
+            m2, m4 = (m2 / n_meas).cpu().numpy(), (m4 / n_meas).cpu().numpy()
+            u = lambda a2, a4: 1.0 - a4.mean() / (3.0 * a2.mean() ** 2)
+            jk = np.array([u(np.delete(m2, r), np.delete(m4, r)) for r in range(R)])
+            U[L, T] = u(m2, m4)
+            err[L, T] = np.sqrt((R - 1) / R * ((jk - jk.mean()) ** 2).sum())
+    print({k: (round(float(U[k]), 4), round(float(err[k]), 4)) for k in U})
+    for a, b in ((32, 64), (64, 128)):
+        lo, mid, hi = temps
+        sig = lambda T: 4.0 * np.hypot(err[a, T], err[b, T])
+        assert U[b, lo] > U[a, lo] - sig(lo), (a, b, U, err)           # ordered side: larger L -> larger U4 (-> 2/3)
+        assert U[b, hi] < U[a, hi] + sig(hi), (a, b, U, err)           # disordered side: larger L -> smaller U4 (-> 0)
+        # the sign of U_b - U_a flips between 2.24 and 2.30, and at T_c the difference is small against both ends:
+        # the crossing lies within +-0.03 of 2.269
+        d_lo, d_mid, d_hi = U[b, lo] - U[a, lo], U[b, mid] - U[a, mid], U[b, hi] - U[a, hi]
+        assert d_lo > sig(lo) and d_hi < -sig(hi), (a, b, U, err)
+        assert abs(d_mid) < 0.35 * min(d_lo, -d_hi) + sig(mid), (a, b, U, err)
+    for L in sizes:
+        assert abs(U[L, 2.269] - 0.61) < 0.04 + 4.0 * err[L, 2.269], (L, U[L, 2.269], err[L, 2.269])   # U* = 0.6107 (periodic square)
