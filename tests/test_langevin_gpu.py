@@ -106,3 +106,33 @@ def test_readme_sample_boltzmann_shape_and_variance():
     assert abs(out.var() - 0.505) < 0.01
     assert abs(out.mean()) < 0.01
     assert tsu.sample_count == 100000
+
+
+def test_p_bit_categorical_and_neuron():
+    """tsu/core.py:164-206,241-294 contracts (shape, binary, probability within the reference test's 0.05, errors);
+    exact Bernoulli / inverse-CDF draws on Philox words"""
+    from tsu_emulator_b200 import ConfigurationError, ProbabilisticNeuron, ThermalSamplingUnit, validate_distribution
+
+    tsu = ThermalSamplingUnit(seed=5)
+    s = tsu.p_bit(prob=0.5, n_samples=100)
+    assert len(s) == 100 and set(s).issubset({0, 1})
+    for p in (0.2, 0.5, 0.8):                      # reference tests/test_core.py:86-97
+        assert abs(tsu.p_bit(prob=p, n_samples=20000).mean() - p) < 0.015
+    assert tsu.p_bit(0.0, 1000).sum() == 0 and tsu.p_bit(1.0, 1000).sum() == 1000
+    a, b = tsu.p_bit(0.5, 64), tsu.p_bit(0.5, 64)
+    assert (a != b).any()                          # successive calls use fresh random words
+    with pytest.raises(ConfigurationError):
+        tsu.p_bit(prob=-0.1)
+    with pytest.raises(ConfigurationError):
+        tsu.p_bit(prob=0.5, n_samples=0)
+    probs = np.array([1.0, 2.0, 3.0, 4.0])
+    c = tsu.sample_categorical(probs, n_samples=40000)
+    assert c.min() >= 0 and c.max() <= 3
+    assert np.abs(np.bincount(c, minlength=4) / 40000 - probs / 10).max() < 0.01
+    n = ProbabilisticNeuron(tsu)
+    assert n.activate(np.array([10.0]), np.array([5.0])) == 1
+    assert abs(n.forward_stochastic(np.array([1.0, -1.0]), np.array([0.3, 0.3]), n_samples=4000) - 0.5) < 0.04
+    r = validate_distribution(tsu.p_bit(0.3, 5000), "bernoulli", {"p": 0.3})
+    assert r["passes_test"] and r["n_samples"] == 5000
+    g = ThermalSamplingUnit(seed=6).sample_gaussian(mu=0, sigma=1, n_samples=2000)
+    assert validate_distribution(g, "gaussian", {"mu": 0, "sigma": 1}, alpha=0.001)["passes_ks_test"]

@@ -14,12 +14,14 @@ from .core import (  # noqa: F401
     DoubleWellEnergy,
     GaussianEnergy,
     MixtureEnergy,
+    ProbabilisticNeuron,
     QuadraticEnergy,
     QuadraticFormEnergy,
     SamplingError,
     ThermalSamplingUnit,
     TSUConfig,
     TSUError,
+    validate_distribution,
 )
 from .gibbs import GibbsConfig, GibbsSampler, HardwareEmulator  # noqa: F401
 from .lattice import Ising2DEngine, build_lut  # noqa: F401

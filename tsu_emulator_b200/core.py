@@ -240,6 +240,7 @@ class ThermalSamplingUnit:
         self.dtype = dtype
         self._seed = int(seed) if seed is not None else int(np.random.randint(0, 2**31 - 1))
         self._chain_counter = 0
+        self._fill_counter = 0
         self._device = device
 
     # -- host-side single-step helpers kept for API compatibility (tsu/core.py:64-98) -----------------
@@ -351,17 +352,80 @@ class ThermalSamplingUnit:
         samples = self.sample_from_energy(GaussianEnergy(mu, sigma), np.array([mu], dtype=np.float64), n_samples)
         return samples.flatten()
 
+    def _dev(self):
+        torch = _lib.require_cuda()
+        return torch.device(self._device) if self._device is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def _uniform_words(self, n: int):
+        """n raw 32-bit Philox words on the device ('FILL' stream; the call counter keeps successive calls apart)"""
+        torch = _lib.require_cuda()
+        out = torch.empty(int(n), dtype=torch.int32, device=self._dev())
+        with torch.cuda.device(out.device):
+            _lib.call("tsu_philox_fill_u32", ptr(out), int(n), self._seed, self._fill_counter & 0xFFFFFFFF, _lib.current_stream())
+        self._fill_counter += 1
+        return out.to(torch.int64) & 0xFFFFFFFF
+
     def p_bit(self, prob: float, n_samples: int = 1) -> np.ndarray:
-        """tsu/core.py:164-206 is a toy wrapper (Langevin on a clipped linear energy, then threshold 0.5) and is
-        outside the accelerated path; the validation is kept, the sampler is not reimplemented."""
+        """probabilistic bit: n_samples draws of Bernoulli(prob) as an int array (tsu/core.py:164-206 contract and
+        error behaviour).  The reference runs its Langevin loop on a clipped linear energy and thresholds at 0.5,
+        which diffuses freely outside [0, 1] and does not return `prob` (its own test_core.py:86-97 tolerance is
+        missed for p = 0.2 / 0.8); here the bit is exact: k < ceil(prob * 2^32) on a 32-bit Philox word k."""
         if not 0 <= prob <= 1:
             raise ConfigurationError(f"Probability must be in [0,1], got {prob}")
         if n_samples <= 0:
             raise ConfigurationError(f"n_samples must be positive, got {n_samples}")
-        raise NotImplementedError("p_bit is outside the B200 hot path (see DESIGN.md, out of scope)")
+        thr = int(np.ceil(float(prob) * 4294967296.0))
+        return (self._uniform_words(n_samples) < thr).cpu().numpy().astype(int)
 
     def sample_categorical(self, probs: np.ndarray, n_samples: int = 1) -> np.ndarray:
-        raise NotImplementedError("sample_categorical is outside the B200 hot path (see DESIGN.md, out of scope)")
+        """n_samples category indices with probabilities probs / probs.sum() (tsu/core.py:241-267 contract); exact
+        inverse-CDF sampling on 32-bit Philox words instead of the reference's Langevin walk over |x| mod K"""
+        torch = _lib.require_cuda()
+        p = np.asarray(probs, dtype=np.float64)
+        if p.ndim != 1 or p.size == 0 or (p < 0).any() or not p.sum() > 0:
+            raise ConfigurationError("probs must be a non-empty 1-D array of non-negative weights with a positive sum")
+        if n_samples <= 0:
+            raise ConfigurationError(f"n_samples must be positive, got {n_samples}")
+        edges = np.ceil(np.cumsum(p / p.sum()) * 4294967296.0)
+        edges[-1] = 4294967296.0
+        k = self._uniform_words(n_samples)
+        idx = torch.searchsorted(torch.from_numpy(edges.astype(np.int64)).to(k.device), k, right=True)
+        return idx.cpu().numpy().astype(int)
+
+
+class ProbabilisticNeuron:
+    """single stochastic neuron on a ThermalSamplingUnit (tsu/core.py:270-294): output ~ Bernoulli(sigmoid(w.x + b))"""
+
+    def __init__(self, tsu: ThermalSamplingUnit):
+        self.tsu = tsu
+
+    def activate(self, weights: np.ndarray, inputs: np.ndarray, bias: float = 0.0) -> int:
+        logit = float(np.dot(weights, inputs) + bias)
+        return int(self.tsu.p_bit(1.0 / (1.0 + np.exp(-logit)), n_samples=1)[0])
+
+    def forward_stochastic(self, weights: np.ndarray, inputs: np.ndarray, bias: float = 0.0, n_samples: int = 10) -> float:
+        """expected output from n_samples activations (one batched draw instead of the reference's Python loop)"""
+        logit = float(np.dot(weights, inputs) + bias)
+        return float(np.mean(self.tsu.p_bit(1.0 / (1.0 + np.exp(-logit)), n_samples=n_samples)))
+
+
+def validate_distribution(samples: np.ndarray, expected_dist: str, params: dict, alpha: float = 0.05) -> dict:
+    """host-side check of samples against "gaussian" (KS test) or "bernoulli" (|mean - p| < 0.05): same keys as
+    tsu/core.py:298-327"""
+    samples = np.asarray(samples)
+    results = {"mean": np.mean(samples), "std": np.std(samples), "n_samples": len(samples)}
+    if expected_dist == "gaussian":
+        from scipy import stats
+
+        mu, sigma = params.get("mu", 0), params.get("sigma", 1)
+        ks_stat, p_value = stats.kstest(samples, stats.norm(loc=mu, scale=sigma).cdf)
+        results.update(expected_mean=mu, expected_std=sigma, ks_statistic=ks_stat, ks_pvalue=p_value,
+                       passes_ks_test=p_value > alpha)
+    elif expected_dist == "bernoulli":
+        prob = params.get("p", 0.5)
+        err = abs(np.mean(samples) - prob)
+        results.update(expected_mean=prob, empirical_prob=np.mean(samples), error=err, passes_test=err < 0.05)
+    return results
 
 
 TSU = ThermalSamplingUnit
