@@ -233,3 +233,22 @@ def test_binder_cumulant_crossing_at_tc():
         assert abs(d_mid) < 0.35 * min(d_lo, -d_hi) + sig(mid), (a, b, U, err)
     for L in sizes:
         assert abs(U[L, 2.269] - 0.61) < 0.04 + 4.0 * err[L, 2.269], (L, U[L, 2.269], err[L, 2.269])   # U* = 0.6107 (periodic square)
+
+
+@pytest.mark.parametrize("rows,cols,periodic", [(50, 50, True), (50, 50, False), (37, 61, False), (256, 256, True)])
+def test_resident_small_lattice_kernel_matches_per_half_sweep_launches(rows, cols, periodic, monkeypatch):
+    """C1-sized lattices run all sweeps of a call in ONE launch (one thread block per replica); the bits must equal
+    the launch-per-half-sweep path (TSU_LATTICE_RESIDENT=0) and the oracle"""
+    kw = dict(n_replicas=3, temperature=2.5, periodic=periodic, seed=77)
+    a = make_engine(rows, cols, **kw)
+    a.init_random()
+    start = a.get_spins(pm1=False)
+    a.sweep(7)
+    monkeypatch.setenv("TSU_LATTICE_RESIDENT", "0")
+    b = make_engine(rows, cols, **kw)
+    b.init_random()
+    b.sweep(7)
+    got = a.get_spins(pm1=False)
+    assert (got == b.get_spins(pm1=False)).all()
+    want = O.checkerboard_sweeps_philox(start[1], 77, 1, 0, 7, 1.0, 0.0, 2.5, periodic)
+    assert (got[1] == want).all()

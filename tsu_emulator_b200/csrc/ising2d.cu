@@ -209,7 +209,33 @@ __global__ void __launch_bounds__(128, MINB) half_sweep_fast_kernel(SweepParams 
   tsu_fast::half_sweep_fast_body(P);
 }
 
-// Generic path: any size, open or periodic edges, ragged last word.  One thread per word.
+// One word of (replica rep, colour, local row i): any size, open or periodic edges, ragged last word.
+__device__ __forceinline__ void generic_update_one(const SweepParams& P, int colour, uint32_t sweep, int rep, int i, int w) {
+  const Geom& g = P.g;
+  const size_t plane = (size_t)g.rows * g.wpr;
+  uint32_t* own = P.state + ((size_t)rep * 2 + colour) * plane;
+  Planes pl;
+  pl.opp = P.state + ((size_t)rep * 2 + (1 - colour)) * plane;
+  pl.halo_top = P.halo_top ? P.halo_top + (size_t)rep * g.wpr : nullptr;
+  pl.halo_bot = P.halo_bot ? P.halo_bot + (size_t)rep * g.wpr : nullptr;
+  const uint32_t* lut = P.lut + (P.lut_index ? (size_t)P.lut_index[rep] * 32 : 0);
+
+  const Hood h = load_hood(pl, g, colour, i, w);
+  if (h.valid == 0u) return;  // padding word (stays 0)
+  const int d_row = 2 + h.has_n + h.has_s;
+  LutRegs L;
+  load_lut_regs(L, lut, d_row);
+  Coords q;
+  q.c0_base = (uint32_t)w | ((uint32_t)colour << 20);
+  q.row_g = (uint32_t)(g.row0 + i);
+  q.sweep = sweep;
+  q.replica = P.replica0 + (uint32_t)rep;
+  q.k0 = P.k0;
+  q.k1 = P.k1;
+  own[(size_t)i * g.wpr + w] = update_word<false>(h.n, h.s, h.c, h.side, L, lut, d_row, h.valid, h.missW, h.missE, q);
+}
+
+// Generic path: one thread per word, one launch per half-sweep.
 __global__ void __launch_bounds__(128) half_sweep_generic_kernel(SweepParams P) {
   const Geom& g = P.g;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -218,29 +244,27 @@ __global__ void __launch_bounds__(128) half_sweep_generic_kernel(SweepParams P) 
   const int rep = (int)(tid / per_rep);
   const int rem = (int)(tid - (long long)rep * per_rep);
   const int i = rem / g.wpr;
-  const int w = rem - i * g.wpr;
+  generic_update_one(P, P.colour, P.sweep, rep, i, rem - i * g.wpr);
+}
 
-  const size_t plane = (size_t)g.rows * g.wpr;
-  uint32_t* own = P.state + ((size_t)rep * 2 + P.colour) * plane;
-  Planes pl;
-  pl.opp = P.state + ((size_t)rep * 2 + (1 - P.colour)) * plane;
-  pl.halo_top = P.halo_top ? P.halo_top + (size_t)rep * g.wpr : nullptr;
-  pl.halo_bot = P.halo_bot ? P.halo_bot + (size_t)rep * g.wpr : nullptr;
-  const uint32_t* lut = P.lut + (P.lut_index ? (size_t)P.lut_index[rep] * 32 : 0);
-
-  const Hood h = load_hood(pl, g, P.colour, i, w);
-  if (h.valid == 0u) return;  // padding word (stays 0)
-  const int d_row = 2 + h.has_n + h.has_s;
-  LutRegs L;
-  load_lut_regs(L, lut, d_row);
-  Coords q;
-  q.c0_base = (uint32_t)w | ((uint32_t)P.colour << 20);
-  q.row_g = (uint32_t)(g.row0 + i);
-  q.sweep = P.sweep;
-  q.replica = P.replica0 + (uint32_t)rep;
-  q.k0 = P.k0;
-  q.k1 = P.k1;
-  own[(size_t)i * g.wpr + w] = update_word<false>(h.n, h.s, h.c, h.side, L, lut, d_row, h.valid, h.missW, h.missE, q);
+// Small lattices (C1: 50 x 50): the whole replica belongs to ONE thread block, which runs both colours of
+// n_sweeps sweeps in a single launch with a block barrier between half-sweeps.  Same words, same Philox
+// coordinates, same bits as the per-half-sweep launches - it only removes 2 n_sweeps - 1 kernel launches,
+// which is all the time there is at this size.
+constexpr int kResidentThreads = 256;
+__global__ void __launch_bounds__(kResidentThreads) sweeps_resident_kernel(SweepParams P, int n_sweeps) {
+  const Geom& g = P.g;
+  const int rep = blockIdx.x;
+  const int per_rep = g.rows * g.wpr;
+  for (int t = 0; t < n_sweeps; ++t) {
+    for (int colour = 0; colour < 2; ++colour) {
+      for (int rem = threadIdx.x; rem < per_rep; rem += kResidentThreads) {
+        const int i = rem / g.wpr;
+        generic_update_one(P, colour, P.sweep + (uint32_t)t, rep, i, rem - i * g.wpr);
+      }
+      __syncthreads();  // the other colour reads what this half-sweep wrote (same SM: L1 is coherent for its own stores)
+    }
+  }
 }
 
 // Parity mode: uniforms injected per site.  One thread per word, one lane at a time.
@@ -510,6 +534,35 @@ int launch_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int
   return e == cudaSuccess ? TSU_OK : (int)e;
 }
 
+// true when a replica is small enough that per-half-sweep launches would be pure launch latency
+bool resident_eligible(int n_replicas, int rows, int cols) {
+  if (const char* e = getenv("TSU_LATTICE_RESIDENT")) {
+    if (atoi(e) == 0) return false;
+  }
+  const long long per_rep = (long long)rows * words_per_row(cols);
+  // <= 16 words per thread and half-sweep, and not enough replicas to fill the GPU with the wide kernels
+  return per_rep <= 16LL * kResidentThreads && (long long)n_replicas * per_rep <= 148LL * 2048;
+}
+
+int launch_resident_sweeps(uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows, int wrap_cols,
+                           const uint32_t* d_lut, const int32_t* d_lut_index, uint64_t seed, uint32_t sweep0, int n_sweeps,
+                           uint32_t replica0, cudaStream_t st) {
+  SweepParams P = {};
+  P.state = d_state;
+  P.lut = d_lut;
+  P.lut_index = d_lut_index;
+  P.g = make_geom(n_replicas, rows, cols, wrap_rows, wrap_cols, 0);
+  P.sweep = sweep0;
+  P.replica0 = replica0;
+  P.k0 = (uint32_t)seed;
+  P.k1 = (uint32_t)(seed >> 32);
+  P.strip_rows = 1;
+  P.n_strips = rows;
+  sweeps_resident_kernel<<<n_replicas, kResidentThreads, 0, st>>>(P, n_sweeps);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? TSU_OK : (int)e;
+}
+
 }  // namespace
 
 extern "C" {
@@ -565,6 +618,9 @@ int tsu_ising2d_sweeps(uint32_t* d_state, int n_replicas, int rows, int cols, in
   TSU_CHECK_ARG(d_state && d_lut && geom_ok(n_replicas, rows, cols) && n_sweeps >= 0);
   TSU_CHECK_ARG(!wrap_cols || (cols % 2 == 0 && cols > 2));
   TSU_CHECK_ARG(!wrap_rows || (rows % 2 == 0 && rows > 2));
+  if (n_sweeps > 0 && resident_eligible(n_replicas, rows, cols))
+    return launch_resident_sweeps(d_state, n_replicas, rows, cols, wrap_rows, wrap_cols, d_lut, d_lut_index, seed, sweep0,
+                                  n_sweeps, replica0, tsu_stream(stream));
   for (int t = 0; t < n_sweeps; ++t) {
     for (int colour = 0; colour < 2; ++colour) {
       int rc = launch_half_sweep(d_state, n_replicas, rows, cols, wrap_rows, wrap_cols, colour, d_lut, d_lut_index,
@@ -714,6 +770,9 @@ int tsu_ising2d_sweeps_jit(int jit_handle, uint32_t* d_state, int n_replicas, in
   TSU_CHECK_ARG(d_state && d_lut && geom_ok(n_replicas, rows, cols) && n_sweeps >= 0);
   TSU_CHECK_ARG(!wrap_cols || (cols % 2 == 0 && cols > 2));
   TSU_CHECK_ARG(!wrap_rows || (rows % 2 == 0 && rows > 2));
+  if (n_sweeps > 0 && resident_eligible(n_replicas, rows, cols))  // launch latency dominates: one launch for everything
+    return launch_resident_sweeps(d_state, n_replicas, rows, cols, wrap_rows, wrap_cols, d_lut, nullptr, seed, sweep0,
+                                  n_sweeps, replica0, tsu_stream(stream));
   void* fn = jit_function(jit_handle);
   for (int t = 0; t < n_sweeps; ++t) {
     for (int colour = 0; colour < 2; ++colour) {
