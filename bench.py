@@ -195,6 +195,14 @@ def profiled_traffic():
     return None
 
 
+def profiled_limiter():
+    """what the committed ncu capture says actually limits the kernel (the HBM fraction alone would mislead)"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "lattice_traffic.json"))).get("limiter")
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------- B200 arm
 def run_b200_arm(args):
     import numpy as np
@@ -362,6 +370,7 @@ def run_b200_arm(args):
                        if getattr(eng, "_jit", 0) > 0 else "half_sweep_fast_kernel"),
             "algorithmic_bytes_per_launch": alg_bytes_per_launch,
             "launch_ms": launch_s * 1e3,
+            "measured_limiter": profiled_limiter(),
         },
         "cpu_baseline": cpu,
         "e2e": e2e,
