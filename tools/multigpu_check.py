@@ -48,5 +48,42 @@ if rank == 0:
 m = drv.observables()
 if rank == 0:
     print("[C4] E/N after 23 sweeps:", float(-(2 * rows * cols - 2 * m[0, 1].item()) / (rows * cols)), flush=True)
+
+# (3) replica exchange: K ladders x R temperatures sharded over the ranks (energies all-gathered, every rank runs the same
+#     deterministic swap pass) must give the observables of the unsharded run
+import torch.distributed  # noqa: E402
+from tsu_emulator_b200.distributed import LatticeTempering  # noqa: E402
+
+temps = np.linspace(2.0, 3.0, 8)
+def run_pt(group_on):
+    fac = lambda n, r0, T: Ising2DEngine(16, 32, n_replicas=n, temperature=T, periodic=True, seed=5, replica0=r0).init_random()
+    if group_on:
+        pt = LatticeTempering(temps, n_ladders=4, engine_factory=fac, n_sweeps=3, swap_interval=2, seed=123)
+    else:  # whole problem on this rank: hide the process group from the driver
+        real = (dist.is_initialized,)
+        dist.is_initialized = lambda: False
+        try:
+            pt = LatticeTempering(temps, n_ladders=4, engine_factory=fac, n_sweeps=3, swap_interval=2, seed=123)
+        finally:
+            dist.is_initialized = real[0]
+    for _ in range(40):
+        pt.step()
+    return pt
+pt = run_pt(world > 1)
+m_sh, e_sh = pt.observables_by_slot()
+sr_sh = pt.slot_replica.cpu().numpy()
+ref = run_pt(False)
+real_init = dist.is_initialized
+dist.is_initialized = lambda: False
+try:
+    m_1, e_1 = ref.observables_by_slot()
+finally:
+    dist.is_initialized = real_init
+ok = torch.tensor([int(np.array_equal(m_sh, m_1) and np.array_equal(e_sh, e_1) and np.array_equal(sr_sh, ref.slot_replica.cpu().numpy()))], device="cuda")
+if world > 1:
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"[tempering] 4 ladders x 8 temperatures sharded over {world} rank(s) == unsharded run: {bool(ok.item())} "
+          f"(swap acceptance {float(pt.stats[1]) / max(1.0, float(pt.stats[0])):.3f})", flush=True)
 if world > 1:
     dist.barrier(); dist.destroy_process_group()
