@@ -105,3 +105,25 @@ def test_compat_shim_exposes_reference_module_paths():
         sys.path.pop(0)
         for k in [k for k in sys.modules if k == "tsu" or k.startswith("tsu.")]:
             del sys.modules[k]
+
+
+def test_p_bit_and_categorical_validation_precedes_device_work():
+    """tsu/core.py:177-180: argument errors are ConfigurationError, raised before anything touches the GPU"""
+    from tsu_emulator_b200 import ConfigurationError, ProbabilisticNeuron, ThermalSamplingUnit, validate_distribution
+
+    tsu = ThermalSamplingUnit(seed=1)
+    for bad in (-0.1, 1.5):
+        with pytest.raises(ConfigurationError, match="Probability must be in"):
+            tsu.p_bit(prob=bad)
+    with pytest.raises(ConfigurationError, match="n_samples must be positive"):
+        tsu.p_bit(prob=0.5, n_samples=0)
+    with pytest.raises(ConfigurationError):
+        tsu.sample_categorical(np.array([]), 3)
+    with pytest.raises(ConfigurationError):
+        tsu.sample_categorical(np.array([0.5, -0.1]), 3)
+    assert ProbabilisticNeuron(tsu).tsu is tsu
+    rng = np.random.default_rng(0)
+    r = validate_distribution(rng.normal(2.0, 3.0, 4000), "gaussian", {"mu": 2.0, "sigma": 3.0})
+    assert r["passes_ks_test"] and abs(r["mean"] - 2.0) < 0.2 and r["expected_std"] == 3.0
+    r = validate_distribution(rng.random(4000) < 0.3, "bernoulli", {"p": 0.3})
+    assert r["passes_test"] and abs(r["empirical_prob"] - 0.3) < 0.03

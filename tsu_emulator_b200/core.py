@@ -381,12 +381,12 @@ class ThermalSamplingUnit:
     def sample_categorical(self, probs: np.ndarray, n_samples: int = 1) -> np.ndarray:
         """n_samples category indices with probabilities probs / probs.sum() (tsu/core.py:241-267 contract); exact
         inverse-CDF sampling on 32-bit Philox words instead of the reference's Langevin walk over |x| mod K"""
-        torch = _lib.require_cuda()
         p = np.asarray(probs, dtype=np.float64)
         if p.ndim != 1 or p.size == 0 or (p < 0).any() or not p.sum() > 0:
             raise ConfigurationError("probs must be a non-empty 1-D array of non-negative weights with a positive sum")
         if n_samples <= 0:
             raise ConfigurationError(f"n_samples must be positive, got {n_samples}")
+        torch = _lib.require_cuda()
         edges = np.ceil(np.cumsum(p / p.sum()) * 4294967296.0)
         edges[-1] = 4294967296.0
         k = self._uniform_words(n_samples)
