@@ -82,8 +82,10 @@ del pt; torch.cuda.empty_cache()
 for dtype in ("float32", "float64"):
     tsu = ThermalSamplingUnit(TSUConfig(temperature=1.0, dt=0.01, friction=1.0, n_burnin=100, n_steps=500), seed=1, dtype=dtype)
     tsu.sample_from_energy(QuadraticEnergy(), np.zeros(10), 1000, as_tensor=True); torch.cuda.synchronize()
-    a, b = ev(); a.record(); x = tsu.sample_from_energy(QuadraticEnergy(), np.zeros(10), 1_000_000, as_tensor=True); b.record()
-    torch.cuda.synchronize(); ms = a.elapsed_time(b)
+    ms = 1e30
+    for _ in range(2):  # best of two (the first full-size call also pays for lazy kernel loading)
+        a, b = ev(); a.record(); x = tsu.sample_from_energy(QuadraticEnergy(), np.zeros(10), 1_000_000, as_tensor=True); b.record()
+        torch.cuda.synchronize(); ms = min(ms, a.elapsed_time(b))
     out.append({"config": "C5-langevin", "workload": f"sample_boltzmann E=sum x^2, dim 10, 1e6 chains, 100+500 steps, {dtype}",
                 "ms": ms, "chain_steps_per_s": 1e6 * 600 / ms * 1e3, "coordinate_updates_per_s": 1e6 * 6000 / ms * 1e3,
                 "variance": float(x.var()), "euler_maruyama_theory": 0.5 / (1 - 0.01)})
