@@ -217,6 +217,24 @@ def run_b200_arm(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the B200 arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # Host side of the end-to-end leg: run this rank (and first-touch its pinned staging buffer) on the CPU cores that
+    # are local to its GPU, so that the N ranks of one box do not pull their uploads across the socket interconnect.
+    cpu_mask0 = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa_note = None
+    if world > 1 and cpu_mask0 is not None:
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            n_words = (os.cpu_count() + 63) // 64
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+            cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1} & cpu_mask0
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                numa_note = f"rank pinned to the {len(cpus)} CPU cores local to its GPU"
+        except Exception as exc:  # no NVML / no permission: keep the inherited mask
+            numa_note = f"cpu affinity unchanged ({type(exc).__name__})"
     json_fd = None
     if world > 1:
         # NCCL prints its version / debug lines on fd 1 (the image sets NCCL_DEBUG=VERSION).  stdout must carry only
@@ -322,12 +340,15 @@ def run_b200_arm(args):
             "ms_per_step": e2e_ms / args.steps,
             "api": "Ising2DEngine: pinned host state -> H2D (16 chunks, overlapped) -> sweep(10) -> observables -> D2H",
             "pinned_host_bytes": int(host.numel() * 4),
+            "host_affinity": numa_note,
         }
         del host
     except Exception as exc:  # e.g. pinned allocation refused
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(exc)}
 
     cpu = None
+    if cpu_mask0 is not None:
+        os.sched_setaffinity(0, cpu_mask0)  # the CPU baseline may use every host core again
     if rank == 0 and not args.no_cpu:
         cpu = cpu_baseline()
     if world > 1:
