@@ -130,7 +130,8 @@ def test_per_replica_temperatures():
 def test_observables_match_oracle():
     rng = np.random.default_rng(5)
     for (rows, cols, periodic, J, h) in [(8, 256, True, 1.0, 0.0), (7, 5, False, 0.7, -0.2), (50, 50, False, 1.0, 0.3),
-                                         (2, 6, True, 1.0, 0.1), (12, 70, True, -1.0, 0.0), (1, 9, False, 1.0, 0.0)]:
+                                         (2, 6, True, 1.0, 0.1), (12, 70, True, -1.0, 0.0), (1, 9, False, 1.0, 0.0),
+                                         (66, 512, True, 1.0, 0.2), (130, 256, True, -0.5, 0.0), (4, 768, True, 1.0, 0.0)]:
         bits = rng.integers(0, 2, (2, rows, cols))
         eng = make_engine(rows, cols, n_replicas=2, coupling=J, field=h, periodic=periodic)
         eng.set_spins(bits)
@@ -138,6 +139,31 @@ def test_observables_match_oracle():
         for r in range(2):
             assert E[r] == pytest.approx(O.energy(bits[r], J, h, periodic), abs=1e-9)
             assert M[r] == pytest.approx(O.magnetization(bits[r]), abs=1e-12)
+
+
+def test_observables_vector_kernel_equals_generic_kernel(monkeypatch):
+    """the 16-byte-vector observables kernel (periodic columns, cols % 256 == 0) against the word-by-word kernel, for a
+    whole lattice and for a row slab that gets its lower neighbour rows from another rank (next_rows)"""
+    import torch
+    rng = np.random.default_rng(9)
+    rows, cols = 96, 1024
+    bits = rng.integers(0, 2, (3, rows, cols))
+    whole = make_engine(rows, cols, n_replicas=3, periodic=True)
+    whole.set_spins(bits)
+    slab = make_engine(40, cols, n_replicas=3, periodic=True, row0=17, global_rows=rows)   # rows 17..56 of the lattice
+    slab.set_spins(bits[:, 17:57, :])
+    below = make_engine(2, cols, n_replicas=3, periodic=True, row0=57, global_rows=rows)  # row 57 in the slab's layout
+    below.set_spins(bits[:, 57:59, :])
+    nxt = below.state[:, :, 0, :].contiguous()
+    fast = [whole.observables_tensor().clone(), slab.observables_tensor(next_rows=nxt).clone(),
+            slab.observables_tensor(next_rows=None).clone()]
+    monkeypatch.setenv("TSU_LATTICE_OBS_GENERIC", "1")
+    slow = [whole.observables_tensor().clone(), slab.observables_tensor(next_rows=nxt).clone(),
+            slab.observables_tensor(next_rows=None).clone()]
+    for f, g in zip(fast, slow):
+        assert torch.equal(f, g)
+    for r in range(3):
+        assert whole.energy()[r] == pytest.approx(O.energy(bits[r], 1.0, 0.0, True), abs=1e-9)
 
 
 def test_large_lattice_properties():

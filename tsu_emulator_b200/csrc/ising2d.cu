@@ -399,6 +399,70 @@ __global__ void __launch_bounds__(256) observables_kernel(const uint32_t* __rest
   }
 }
 
+// Same counts for periodic columns with full words (cols % 256 == 0), at HBM speed: a thread owns a 4-word column
+// strip of BOTH colour planes and walks down its rows with a rolling (row i, row i+1) window, so every word is
+// loaded once as a 16-byte vector.  In a row exactly one colour has odd own columns (east neighbour = next lane of
+// the other plane, i.e. a 1-bit funnel shift that needs one extra word); the other colour's east neighbour is the
+// same lane.  The south neighbour of (colour, row i, lane) is (other colour, row i+1, same lane).
+__global__ void __launch_bounds__(128) observables_fast_kernel(const uint32_t* __restrict__ state, Geom g,
+                                                              const uint32_t* __restrict__ next_rows, int strip_rows,
+                                                              int n_strips, unsigned long long* out) {
+  const int nvec = g.wpr >> 2;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_rep = n_strips * nvec;
+  const int per_rep_pad = (per_rep + 31) & ~31;  // warps never straddle replicas
+  const int rep = (int)(tid / per_rep_pad);
+  if (rep >= g.n_replicas) return;
+  const int rem = (int)(tid - (long long)rep * per_rep_pad);
+  unsigned ups = 0, anti = 0;
+  if (rem < per_rep) {
+    const int strip = rem / nvec, w0 = 4 * (rem - strip * nvec);
+    const int r_begin = strip * strip_rows, r_end = min(g.rows, r_begin + strip_rows);
+    const int w_next = (w0 + 4 == g.wpr) ? 0 : w0 + 4;
+    const size_t plane = (size_t)g.rows * g.wpr;
+    const uint32_t* pl[2] = {state + (size_t)rep * 2 * plane, state + ((size_t)rep * 2 + 1) * plane};
+    Planes opp[2];  // opp[c] = the plane that is NOT colour c (south rows beyond the local rows come from next_rows)
+    for (int c = 0; c < 2; ++c) {
+      opp[c].opp = pl[1 - c];
+      opp[c].halo_top = nullptr;
+      opp[c].halo_bot = next_rows ? next_rows + ((size_t)rep * 2 + (1 - c)) * g.wpr : nullptr;
+    }
+    uint4 a[2];
+    a[0] = *reinterpret_cast<const uint4*>(pl[0] + (size_t)r_begin * g.wpr + w0);
+    a[1] = *reinterpret_cast<const uint4*>(pl[1] + (size_t)r_begin * g.wpr + w0);
+    for (int i = r_begin; i < r_end; ++i) {
+      // row i + 1 of both planes (the south neighbours), or nothing below an open last row
+      const uint32_t* s1 = opp_row(opp[0], g, i + 1);  // plane 1 at row i+1 = south of colour 0
+      const uint32_t* s0 = opp_row(opp[1], g, i + 1);  // plane 0 at row i+1 = south of colour 1
+      uint4 b[2] = {a[0], a[1]};
+      if (s0) b[0] = *reinterpret_cast<const uint4*>(s0 + w0);
+      if (s1) b[1] = *reinterpret_cast<const uint4*>(s1 + w0);
+      const int odd = 1 - ((g.row0 + i) & 1);  // colour `odd` has odd own columns in this row: col = 2 lane + 1
+      const uint32_t extra = pl[1 - odd][(size_t)i * g.wpr + w_next];  // next word of the plane the odd colour looks at
+      const uint32_t x0[4] = {a[0].x, a[0].y, a[0].z, a[0].w}, x1[4] = {a[1].x, a[1].y, a[1].z, a[1].w};
+      const uint32_t* own_odd = odd ? x1 : x0;   // colour with the shifted east neighbour
+      const uint32_t* own_even = odd ? x0 : x1;
+      // (own_even is also the plane the odd colour looks at, and vice versa)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t nxt = k < 3 ? own_even[k + 1] : extra;
+        const uint32_t east_odd = __funnelshift_r(own_even[k], nxt, 1);
+        ups += __popc(x0[k]) + __popc(x1[k]);
+        anti += __popc(own_odd[k] ^ east_odd) + __popc(own_even[k] ^ own_odd[k]);
+      }
+      if (s1) anti += __popc(a[0].x ^ b[1].x) + __popc(a[0].y ^ b[1].y) + __popc(a[0].z ^ b[1].z) + __popc(a[0].w ^ b[1].w);
+      if (s0) anti += __popc(a[1].x ^ b[0].x) + __popc(a[1].y ^ b[0].y) + __popc(a[1].z ^ b[0].z) + __popc(a[1].w ^ b[0].w);
+      a[0] = b[0];
+      a[1] = b[1];
+    }
+  }
+  const unsigned long long u64 = tsu_warp_sum((unsigned long long)ups), a64 = tsu_warp_sum((unsigned long long)anti);
+  if ((threadIdx.x & 31) == 0) {
+    if (u64) atomicAdd(out + 2 * rep, u64);
+    if (a64) atomicAdd(out + 2 * rep + 1, a64);
+  }
+}
+
 __global__ void energy_from_obs_kernel(const unsigned long long* __restrict__ obs, int n, double J, double h,
                                        long long n_bonds, long long n_sites, double* energy) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -666,6 +730,16 @@ int tsu_ising2d_observables(const uint32_t* d_state, int n_replicas, int rows, i
   cudaStream_t st = tsu_stream(stream);
   cudaError_t e = cudaMemsetAsync(d_out, 0, sizeof(unsigned long long) * 2 * (size_t)n_replicas, st);
   if (e != cudaSuccess) return (int)e;
+  if (wrap_cols && cols % 256 == 0 && !getenv("TSU_LATTICE_OBS_GENERIC")) {
+    const int nvec = g.wpr / 4;
+    int strip = 64;  // long strips re-read one row in `strip`; short ones fill the GPU for small batches
+    while (strip > 1 && (long long)n_replicas * nvec * ((rows + strip - 1) / strip) < 148LL * 2048) strip >>= 1;
+    const int n_strips = (rows + strip - 1) / strip;
+    const long long per_rep_pad = ((long long)n_strips * nvec + 31) / 32 * 32;
+    observables_fast_kernel<<<blocks_for((long long)n_replicas * per_rep_pad, 128), 128, 0, st>>>(d_state, g, d_next_rows,
+                                                                                                strip, n_strips, d_out);
+    TSU_RETURN_LAUNCH_STATUS();
+  }
   const long long n_words = 2LL * rows * g.wpr;
   long long bx = (n_words + 255) / 256;
   const long long cap = (148LL * 8 + n_replicas - 1) / n_replicas;  // about 8 CTAs per SM in total
