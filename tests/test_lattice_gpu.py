@@ -71,8 +71,10 @@ PHILOX_CASES = [
 ]
 
 
+@pytest.mark.parametrize("resident", ["1", "0"])   # one-launch resident kernel / one launch per half-sweep
 @pytest.mark.parametrize("rows,cols,periodic,T,J,h", PHILOX_CASES)
-def test_philox_mode_is_bit_exact_with_oracle(rows, cols, periodic, T, J, h):
+def test_philox_mode_is_bit_exact_with_oracle(rows, cols, periodic, T, J, h, resident, monkeypatch):
+    monkeypatch.setenv("TSU_LATTICE_RESIDENT", resident)
     n_rep, n_sweeps, seed = 2, 3, 1234
     eng = make_engine(rows, cols, n_replicas=n_rep, coupling=J, field=h, temperature=T, periodic=periodic,
                       seed=seed, replica0=7)
@@ -103,8 +105,10 @@ def test_philox_and_injected_paths_agree_on_philox_uniforms():
     assert (a.get_spins() == b.get_spins()).all()
 
 
-def test_stragglers_exercised():
-    """thresholds whose top byte ties often: every lane with top-8-bit tie must use the low bits"""
+def test_stragglers_exercised(monkeypatch):
+    """thresholds whose top byte ties often: every lane with top-8-bit tie must use the low bits (wide kernel: the
+    tie queue; a lattice this small would otherwise take the resident kernel)"""
+    monkeypatch.setenv("TSU_LATTICE_RESIDENT", "0")
     rows, cols, seed = 64, 1024, 77
     eng = make_engine(rows, cols, temperature=2.269, periodic=True, seed=seed)
     eng.init_random()
@@ -197,10 +201,14 @@ def test_cold_lattice_stays_ordered_and_hot_disorders():
 def test_jit_specialised_and_prebuilt_kernels_agree(monkeypatch):
     """the NVRTC table-specialised build of the fast kernel and the prebuilt jump-table kernel are the same function"""
     import torch
-    rows, cols, seed = 64, 512, 31
+    rows, cols, seed = 320, 1024, 31   # too large for the resident kernel: the wide kernels do the work
     a = make_engine(rows, cols, n_replicas=3, temperature=2.269, periodic=True, seed=seed)
-    if a._jit <= 0:
+    assert a._jit == 0                 # small lattice: no automatic compile (1-2 s per temperature would not pay back)
+    if not a.specialise():
         pytest.skip("NVRTC specialisation unavailable here: " + getattr(a, "_jit_log", ""))
+    small = make_engine(50, 50, temperature=2.269, periodic=True, seed=seed)
+    assert not small.specialise()      # the generic kernels have no specialised form
+    monkeypatch.setenv("TSU_B200_JIT", "1")   # from here on: compile at set_temperature whatever the size
     monkeypatch.setenv("TSU_B200_NO_JIT", "1")
     b = make_engine(rows, cols, n_replicas=3, temperature=2.269, periodic=True, seed=seed)
     assert b._jit == 0

@@ -140,7 +140,31 @@ class Ising2DEngine:
         else:
             self.lut_index = torch.from_numpy(inv.astype(np.int32)).to(self.device)
         self._lut_temps = uniq
-        self._jit = self._jit_prepare(luts[0]) if temps.size == 1 else 0
+        self._jit = self._jit_prepare(luts[0]) if temps.size == 1 and self._jit_worthwhile() else 0
+
+    # NVRTC needs 1-2 s per new temperature and the specialised kernel is ~17 % faster, so it is compiled
+    # automatically only where it can pay back within seconds: the wide periodic kernel on >= 2^28 sites.
+    JIT_MIN_SITES = 1 << 28
+
+    def _jit_worthwhile(self, force: bool = False) -> bool:
+        import os
+
+        if os.environ.get("TSU_B200_NO_JIT"):
+            return False
+        wide = self.wrap_cols and self.cols % 256 == 0 and (self.wrap_rows or self.is_slab)
+        if not wide:
+            return False  # only the wide periodic kernel has a specialised form
+        if force or os.environ.get("TSU_B200_JIT"):
+            return True
+        return self.n_replicas * self.rows * self.cols >= self.JIT_MIN_SITES
+
+    def specialise(self) -> bool:
+        """compile (or fetch from the per-process cache) the half-sweep kernel specialised for the current temperature
+        now, whatever the lattice size; returns whether the specialised kernel is in use.  Results are bit-identical."""
+        if self.lut_index is None and self._jit_worthwhile(force=True):
+            lut_host = self.lut[0].cpu().numpy().view(np.uint32)
+            self._jit = self._jit_prepare(lut_host)
+        return self._jit > 0
 
     def _jit_prepare(self, lut_host: np.ndarray) -> int:
         """table-specialised build of the fast kernel (0 = unavailable: the prebuilt kernels are used)"""
