@@ -89,7 +89,10 @@ int tsu_ising2d_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols
                            const int32_t* d_lut_index, uint64_t seed, uint32_t sweep,
                            uint32_t replica0, int row0, const uint32_t* d_halo_top,
                            const uint32_t* d_halo_bot, uintptr_t stream);
-/* n_sweeps full sweeps (black then white), sweep indices sweep0 .. sweep0+n_sweeps-1, no halos. */
+/* n_sweeps full sweeps (black then white), sweep indices sweep0 .. sweep0+n_sweeps-1, no halos.
+ * Two launches per sweep; lattices of at most 4096 words per replica in batches that would not fill the GPU
+ * (BASELINE config 1: 50 x 50) run ALL sweeps of the call in ONE launch, one thread block per replica.  Same
+ * bits either way (TSU_LATTICE_RESIDENT=0 disables the single-launch form). */
 int tsu_ising2d_sweeps(uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows,
                        int wrap_cols, const uint32_t* d_lut, const int32_t* d_lut_index,
                        uint64_t seed, uint32_t sweep0, int n_sweeps, uint32_t replica0,
