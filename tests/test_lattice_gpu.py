@@ -68,6 +68,10 @@ PHILOX_CASES = [
     (1, 9, False, 1.5, 1.0, 0.0),
     (9, 1, False, 1.5, 1.0, 0.2),
     (3, 130, False, 2.269, 1.0, 0.0),
+    (10, 256, False, 2.269, 1.0, 0.0),  # open lattices with full words: wide kernel + rim pass
+    (64, 512, False, 2.0, 1.0, 0.15),
+    (5, 768, False, 3.0, -1.0, 0.0),
+    (2, 256, False, 1.5, 1.0, 0.0),     # no row has both vertical neighbours: generic kernel
 ]
 
 
@@ -168,6 +172,39 @@ def test_observables_vector_kernel_equals_generic_kernel(monkeypatch):
         assert torch.equal(f, g)
     for r in range(3):
         assert whole.energy()[r] == pytest.approx(O.energy(bits[r], 1.0, 0.0, True), abs=1e-9)
+
+
+def test_open_lattice_wide_kernel_plus_rim_equals_generic_kernel(monkeypatch):
+    """open boundaries (the IsingGrid default) on full-word lattices: wide kernel for the rows with both vertical
+    neighbours + rim pass with the true geometry == the word-by-word generic kernel == the oracle; also for a row slab
+    that has a neighbour slab on one side only"""
+    import torch
+    monkeypatch.setenv("TSU_LATTICE_RESIDENT", "0")
+    rows, cols, seed = 66, 1024, 5
+    kw = dict(n_replicas=3, temperature=2.269, periodic=False, seed=seed, field=0.1)
+    a = make_engine(rows, cols, **kw).init_random()
+    start = a.get_spins(pm1=False)
+    a.sweep(4)
+    monkeypatch.setenv("TSU_LATTICE_OPEN_GENERIC", "1")
+    b = make_engine(rows, cols, **kw).init_random()
+    b.sweep(4)
+    monkeypatch.delenv("TSU_LATTICE_OPEN_GENERIC")
+    assert torch.equal(a.state, b.state)
+    want = O.checkerboard_sweeps_philox(start[2], seed, 2, 0, 4, 1.0, 0.1, 2.269, False)
+    assert (a.get_spins(pm1=False)[2] == want).all()
+    # bottom slab of an open lattice: halo above, open edge below
+    top = a.state[:, :, 40, :].contiguous()
+    for generic in ("", "1"):
+        if generic:
+            monkeypatch.setenv("TSU_LATTICE_OPEN_GENERIC", "1")
+        slab = make_engine(25, cols, n_replicas=3, temperature=2.269, periodic=False, seed=seed, row0=41, global_rows=rows)
+        slab.state.copy_(a.state[:, :, 41:66, :])
+        for colour in (0, 1):
+            slab.half_sweep(colour, halo_top=top[:, 1 - colour, :].contiguous(), halo_bot=None)
+        if generic:
+            assert torch.equal(slab.state, ref_state)
+        else:
+            ref_state = slab.state.clone()
 
 
 def test_large_lattice_properties():

@@ -267,6 +267,31 @@ __global__ void __launch_bounds__(kResidentThreads) sweeps_resident_kernel(Sweep
   }
 }
 
+// Open boundaries with full words (cols % 256 == 0): the wide kernel updates every row that has both vertical
+// neighbours as if the columns wrapped; this pass then recomputes, with the true geometry and degree tables, the rim it
+// got wrong or skipped: rows [0, rb) and [re, rows) completely and, for open columns, the first and last word of the
+// rows in between.  Both passes read only the other colour, so the order of the two launches is the only dependency.
+__global__ void __launch_bounds__(128) half_sweep_rim_kernel(SweepParams P, int rb, int re, int open_cols) {
+  const Geom& g = P.g;
+  const int full_rows = rb + (g.rows - re);
+  const long long per_rep = (long long)full_rows * g.wpr + (open_cols ? 2LL * (re - rb) : 0LL);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= per_rep * g.n_replicas) return;
+  const int rep = (int)(tid / per_rep);
+  const int rem = (int)(tid - (long long)rep * per_rep);
+  int i, w;
+  if (rem < full_rows * g.wpr) {
+    const int r = rem / g.wpr;
+    w = rem - r * g.wpr;
+    i = r < rb ? r : re + (r - rb);
+  } else {
+    const int e = rem - full_rows * g.wpr;
+    i = rb + (e >> 1);
+    w = (e & 1) ? g.wpr - 1 : 0;
+  }
+  generic_update_one(P, P.colour, P.sweep, rep, i, w);
+}
+
 // Parity mode: uniforms injected per site.  One thread per word, one lane at a time.
 __global__ void __launch_bounds__(128) half_sweep_injected_kernel(SweepParams P, const uint32_t* __restrict__ uniforms) {
   const Geom& g = P.g;
@@ -561,19 +586,29 @@ int launch_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int
   P.replica0 = replica0;
   P.k0 = (uint32_t)seed;
   P.k1 = (uint32_t)(seed >> 32);
+  P.row_begin = 0;
+  P.row_end = rows;
   P.debug_flags = 0;
   if (const char* e = getenv("TSU_LATTICE_DEBUG")) P.debug_flags = atoi(e);
-  const bool rows_closed = (wrap_rows && !d_halo_top && !d_halo_bot) || (d_halo_top && d_halo_bot);
-  const bool fast = wrap_cols && (cols % 256 == 0) && rows_closed;
+  // rows that have a north / south neighbour (exactly the cases opp_row() resolves): the wide kernel takes those,
+  // columns treated as periodic; what that gets wrong on open lattices is redone by the rim pass
+  const bool north_ok = d_halo_top || wrap_rows, south_ok = d_halo_bot || wrap_rows;
+  const int rb = north_ok ? 0 : 1, re = south_ok ? rows : rows - 1;
+  const bool need_rim = rb > 0 || re < rows || !wrap_cols;
+  bool fast = (cols % 256 == 0) && re - rb >= 1;
+  if (need_rim && getenv("TSU_LATTICE_OPEN_GENERIC")) fast = false;
   if (fast) {
     const int nvec = P.g.wpr / 4;
+    const int frows = re - rb;
     // strips long enough to amortise the two halo rows, short enough to fill 148 SMs x 16 warps
     const long long target_threads = 148LL * 2048;
     int strip = 64;
-    while (strip > 1 && (long long)n_replicas * nvec * ((rows + strip - 1) / strip) < target_threads) strip >>= 1;
+    while (strip > 1 && (long long)n_replicas * nvec * ((frows + strip - 1) / strip) < target_threads) strip >>= 1;
     if (const char* e = getenv("TSU_LATTICE_STRIP")) strip = atoi(e) > 0 ? atoi(e) : strip;
     P.strip_rows = strip;
-    P.n_strips = (rows + strip - 1) / strip;
+    P.n_strips = (frows + strip - 1) / strip;
+    P.row_begin = rb;
+    P.row_end = re;
     const long long per_rep_pad = ((long long)P.n_strips * nvec + 31) / 32 * 32;  // warps never straddle replicas
     const long long total = (long long)n_replicas * per_rep_pad;
     int minb = 4;
@@ -582,12 +617,15 @@ int launch_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int
     if (jit_fn && !d_lut_index) {  // table-specialised build of the same kernel body
       void* args[] = {&P};
       int rc = g_jit.cuLaunchKernel(jit_fn, grid, 1, 1, 128, 1, 1, 0, (void*)st, args, nullptr);
-      return rc == 0 ? TSU_OK : 999;  // CUDA_ERROR_UNKNOWN for a driver-API launch failure
-    }
-    if (minb == 3) half_sweep_fast_kernel<3><<<grid, 128, 0, st>>>(P);
+      if (rc != 0) return 999;  // CUDA_ERROR_UNKNOWN for a driver-API launch failure
+    } else if (minb == 3) half_sweep_fast_kernel<3><<<grid, 128, 0, st>>>(P);
     else if (minb == 5) half_sweep_fast_kernel<5><<<grid, 128, 0, st>>>(P);
     else if (minb == 6) half_sweep_fast_kernel<6><<<grid, 128, 0, st>>>(P);
     else half_sweep_fast_kernel<4><<<grid, 128, 0, st>>>(P);
+    if (need_rim) {
+      const long long per_rep = (long long)(rb + rows - re) * P.g.wpr + (wrap_cols ? 0LL : 2LL * frows);
+      half_sweep_rim_kernel<<<blocks_for(per_rep * n_replicas, 128), 128, 0, st>>>(P, rb, re, wrap_cols ? 0 : 1);
+    }
   } else {
     P.strip_rows = 1;
     P.n_strips = rows;

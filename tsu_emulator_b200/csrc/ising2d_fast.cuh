@@ -74,6 +74,7 @@ struct SweepParams {
   uint32_t sweep, replica0, k0, k1;
   int strip_rows;  // rows per thread strip (fast path)
   int n_strips;    // strips per replica (fast path)
+  int row_begin, row_end;  // local rows the fast path updates (rows without a north / south neighbour are left to the rim pass)
   int debug_flags; // experiments only (TSU_LATTICE_DEBUG): bit0 = skip tie resolution (WRONG results)
 };
 
@@ -180,8 +181,8 @@ __device__ __forceinline__ void half_sweep_fast_body(const SweepParams& P) {
   const bool active = rem < per_rep;
   const int strip = active ? rem / nvec : 0;
   const int v = active ? rem - strip * nvec : 0;
-  const int r_begin = strip * P.strip_rows;
-  const int r_end = active ? min(g.rows, r_begin + P.strip_rows) : r_begin;
+  const int r_begin = P.row_begin + strip * P.strip_rows;
+  const int r_end = active ? min(P.row_end, r_begin + P.strip_rows) : r_begin;
   const unsigned lane = threadIdx.x & 31u;
   TieQueue* tqs = tie_queues[threadIdx.x >> 5];
   if (lane == 0) {

@@ -143,7 +143,7 @@ class Ising2DEngine:
         self._jit = self._jit_prepare(luts[0]) if temps.size == 1 and self._jit_worthwhile() else 0
 
     # NVRTC needs 1-2 s per new temperature and the specialised kernel is ~17 % faster, so it is compiled
-    # automatically only where it can pay back within seconds: the wide periodic kernel on >= 2^28 sites.
+    # automatically only where it can pay back within seconds: the wide full-word kernel on >= 2^28 sites.
     JIT_MIN_SITES = 1 << 28
 
     def _jit_worthwhile(self, force: bool = False) -> bool:
@@ -151,9 +151,9 @@ class Ising2DEngine:
 
         if os.environ.get("TSU_B200_NO_JIT"):
             return False
-        wide = self.wrap_cols and self.cols % 256 == 0 and (self.wrap_rows or self.is_slab)
+        wide = self.cols % 256 == 0 and self.rows >= 3
         if not wide:
-            return False  # only the wide periodic kernel has a specialised form
+            return False  # only the wide full-word kernel has a specialised form (open rims run the generic kernel)
         if force or os.environ.get("TSU_B200_JIT"):
             return True
         return self.n_replicas * self.rows * self.cols >= self.JIT_MIN_SITES
