@@ -139,7 +139,8 @@ def test_observables_match_oracle():
     rng = np.random.default_rng(5)
     for (rows, cols, periodic, J, h) in [(8, 256, True, 1.0, 0.0), (7, 5, False, 0.7, -0.2), (50, 50, False, 1.0, 0.3),
                                          (2, 6, True, 1.0, 0.1), (12, 70, True, -1.0, 0.0), (1, 9, False, 1.0, 0.0),
-                                         (66, 512, True, 1.0, 0.2), (130, 256, True, -0.5, 0.0), (4, 768, True, 1.0, 0.0)]:
+                                         (66, 512, True, 1.0, 0.2), (130, 256, True, -0.5, 0.0), (4, 768, True, 1.0, 0.0),
+                                         (66, 512, False, 1.0, 0.2), (3, 256, False, -0.5, 0.1), (1, 256, False, 1.0, 0.0)]:
         bits = rng.integers(0, 2, (2, rows, cols))
         eng = make_engine(rows, cols, n_replicas=2, coupling=J, field=h, periodic=periodic)
         eng.set_spins(bits)

@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(256) observables_kernel(const uint32_t* __rest
   }
 }
 
-// Same counts for periodic columns with full words (cols % 256 == 0), at HBM speed: a thread owns a 4-word column
+// Same counts for lattices with full words (cols % 256 == 0; periodic or open), at HBM speed: a thread owns a 4-word column
 // strip of BOTH colour planes and walks down its rows with a rolling (row i, row i+1) window, so every word is
 // loaded once as a 16-byte vector.  In a row exactly one colour has odd own columns (east neighbour = next lane of
 // the other plane, i.e. a 1-bit funnel shift that needs one extra word); the other colour's east neighbour is the
@@ -472,8 +472,10 @@ __global__ void __launch_bounds__(128) observables_fast_kernel(const uint32_t* _
       for (int k = 0; k < 4; ++k) {
         const uint32_t nxt = k < 3 ? own_even[k + 1] : extra;
         const uint32_t east_odd = __funnelshift_r(own_even[k], nxt, 1);
+        // open columns: the last site of a row with odd own columns has no east neighbour
+        const uint32_t has_east = (k == 3 && !g.wrap_cols && w0 + 4 == g.wpr) ? 0x7fffffffu : 0xffffffffu;
         ups += __popc(x0[k]) + __popc(x1[k]);
-        anti += __popc(own_odd[k] ^ east_odd) + __popc(own_even[k] ^ own_odd[k]);
+        anti += __popc((own_odd[k] ^ east_odd) & has_east) + __popc(own_even[k] ^ own_odd[k]);
       }
       if (s1) anti += __popc(a[0].x ^ b[1].x) + __popc(a[0].y ^ b[1].y) + __popc(a[0].z ^ b[1].z) + __popc(a[0].w ^ b[1].w);
       if (s0) anti += __popc(a[1].x ^ b[0].x) + __popc(a[1].y ^ b[0].y) + __popc(a[1].z ^ b[0].z) + __popc(a[1].w ^ b[0].w);
@@ -768,7 +770,7 @@ int tsu_ising2d_observables(const uint32_t* d_state, int n_replicas, int rows, i
   cudaStream_t st = tsu_stream(stream);
   cudaError_t e = cudaMemsetAsync(d_out, 0, sizeof(unsigned long long) * 2 * (size_t)n_replicas, st);
   if (e != cudaSuccess) return (int)e;
-  if (wrap_cols && cols % 256 == 0 && !getenv("TSU_LATTICE_OBS_GENERIC")) {
+  if (cols % 256 == 0 && !getenv("TSU_LATTICE_OBS_GENERIC")) {
     const int nvec = g.wpr / 4;
     int strip = 64;  // long strips re-read one row in `strip`; short ones fill the GPU for small batches
     while (strip > 1 && (long long)n_replicas * nvec * ((rows + strip - 1) / strip) < 148LL * 2048) strip >>= 1;
