@@ -72,6 +72,11 @@ PHILOX_CASES = [
     (64, 512, False, 2.0, 1.0, 0.15),
     (5, 768, False, 3.0, -1.0, 0.0),
     (2, 256, False, 1.5, 1.0, 0.0),     # no row has both vertical neighbours: generic kernel
+    (10, 300, True, 2.269, 1.0, 0.0),   # ragged rows: wide kernel on the full 4-word groups + rim pass on the rest
+    (9, 1000, False, 2.0, 1.0, 0.1),
+    (6, 2050, True, 2.5, -1.0, 0.0),
+    (7, 257, False, 1.5, 1.0, 0.0),
+    (8, 510, True, 2.0, 1.0, 0.2),
 ]
 
 
@@ -181,18 +186,22 @@ def test_open_lattice_wide_kernel_plus_rim_equals_generic_kernel(monkeypatch):
     that has a neighbour slab on one side only"""
     import torch
     monkeypatch.setenv("TSU_LATTICE_RESIDENT", "0")
-    rows, cols, seed = 66, 1024, 5
-    kw = dict(n_replicas=3, temperature=2.269, periodic=False, seed=seed, field=0.1)
-    a = make_engine(rows, cols, **kw).init_random()
-    start = a.get_spins(pm1=False)
+    seed = 5
+    for rows, cols, periodic in ((66, 1024, False), (40, 1000, True), (33, 1379, False)):
+        kw = dict(n_replicas=3, temperature=2.269, periodic=periodic, seed=seed, field=0.1)
+        a = make_engine(rows, cols, **kw).init_random()
+        start = a.get_spins(pm1=False)
+        a.sweep(4)
+        monkeypatch.setenv("TSU_LATTICE_OPEN_GENERIC", "1")
+        b = make_engine(rows, cols, **kw).init_random()
+        b.sweep(4)
+        monkeypatch.delenv("TSU_LATTICE_OPEN_GENERIC")
+        assert torch.equal(a.state, b.state), (rows, cols, periodic)
+        want = O.checkerboard_sweeps_philox(start[2], seed, 2, 0, 4, 1.0, 0.1, 2.269, periodic)
+        assert (a.get_spins(pm1=False)[2] == want).all(), (rows, cols, periodic)
+    rows, cols = 66, 1024
+    a = make_engine(rows, cols, n_replicas=3, temperature=2.269, periodic=False, seed=seed, field=0.1).init_random()
     a.sweep(4)
-    monkeypatch.setenv("TSU_LATTICE_OPEN_GENERIC", "1")
-    b = make_engine(rows, cols, **kw).init_random()
-    b.sweep(4)
-    monkeypatch.delenv("TSU_LATTICE_OPEN_GENERIC")
-    assert torch.equal(a.state, b.state)
-    want = O.checkerboard_sweeps_philox(start[2], seed, 2, 0, 4, 1.0, 0.1, 2.269, False)
-    assert (a.get_spins(pm1=False)[2] == want).all()
     # bottom slab of an open lattice: halo above, open edge below
     top = a.state[:, :, 40, :].contiguous()
     for generic in ("", "1"):

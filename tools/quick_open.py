@@ -6,7 +6,7 @@ from tsu_emulator_b200.lattice import Ising2DEngine
 n_rep = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
 n_sw = int(sys.argv[3]) if len(sys.argv) > 3 else 5
-for periodic, cols in ((False, L), (True, L + 2), (True, L)):
+for periodic, cols in ((False, L), (True, L + 2), (False, L + 1), (True, L)):
     eng = Ising2DEngine(L, cols, n_replicas=n_rep, temperature=2.269, periodic=periodic, seed=1).init_random()
     eng.sweep(2); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -267,14 +267,16 @@ __global__ void __launch_bounds__(kResidentThreads) sweeps_resident_kernel(Sweep
   }
 }
 
-// Open boundaries with full words (cols % 256 == 0): the wide kernel updates every row that has both vertical
-// neighbours as if the columns wrapped; this pass then recomputes, with the true geometry and degree tables, the rim it
+// Open boundaries and / or ragged rows: the wide kernel updates, in every row that has both vertical neighbours, the
+// 4-word groups whose lanes all exist, as if the columns wrapped at a word boundary; this pass then recomputes, with the true geometry and degree tables, the rim it
 // got wrong or skipped: rows [0, rb) and [re, rows) completely and, for open columns, the first and last word of the
 // rows in between.  Both passes read only the other colour, so the order of the two launches is the only dependency.
-__global__ void __launch_bounds__(128) half_sweep_rim_kernel(SweepParams P, int rb, int re, int open_cols) {
+__global__ void __launch_bounds__(128) half_sweep_rim_kernel(SweepParams P, int rb, int re, int head, int tail_begin) {
+  // rim of a row in [rb, re): word 0 if `head`, and the words tail_begin .. wpr-1
   const Geom& g = P.g;
   const int full_rows = rb + (g.rows - re);
-  const long long per_rep = (long long)full_rows * g.wpr + (open_cols ? 2LL * (re - rb) : 0LL);
+  const int per_row = head + (g.wpr - tail_begin);
+  const long long per_rep = (long long)full_rows * g.wpr + (long long)per_row * (re - rb);
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= per_rep * g.n_replicas) return;
   const int rep = (int)(tid / per_rep);
@@ -286,8 +288,9 @@ __global__ void __launch_bounds__(128) half_sweep_rim_kernel(SweepParams P, int 
     i = r < rb ? r : re + (r - rb);
   } else {
     const int e = rem - full_rows * g.wpr;
-    i = rb + (e >> 1);
-    w = (e & 1) ? g.wpr - 1 : 0;
+    const int r = e / per_row, k = e - r * per_row;
+    i = rb + r;
+    w = (head && k == 0) ? 0 : tail_begin + (k - head);
   }
   generic_update_one(P, P.colour, P.sweep, rep, i, w);
 }
@@ -590,18 +593,24 @@ int launch_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int
   P.k1 = (uint32_t)(seed >> 32);
   P.row_begin = 0;
   P.row_end = rows;
+  P.nvec_fast = P.g.wpr / 4;
   P.debug_flags = 0;
   if (const char* e = getenv("TSU_LATTICE_DEBUG")) P.debug_flags = atoi(e);
   // rows that have a north / south neighbour (exactly the cases opp_row() resolves): the wide kernel takes those,
   // columns treated as periodic; what that gets wrong on open lattices is redone by the rim pass
   const bool north_ok = d_halo_top || wrap_rows, south_ok = d_halo_bot || wrap_rows;
   const int rb = north_ok ? 0 : 1, re = south_ok ? rows : rows - 1;
-  const bool need_rim = rb > 0 || re < rows || !wrap_cols;
-  bool fast = (cols % 256 == 0) && re - rb >= 1;
+  // words that are full for both row parities: floor(cols / 2) lanes exist in every row of either colour
+  const int full_words = (cols / 2) / 32;
+  const bool ragged = cols % 256 != 0;
+  const int nvec_f = ragged ? full_words / 4 : P.g.wpr / 4;
+  const bool need_rim = rb > 0 || re < rows || !wrap_cols || ragged;
+  bool fast = nvec_f >= 1 && re - rb >= 1;
   if (need_rim && getenv("TSU_LATTICE_OPEN_GENERIC")) fast = false;
   if (fast) {
-    const int nvec = P.g.wpr / 4;
+    const int nvec = nvec_f;
     const int frows = re - rb;
+    P.nvec_fast = nvec_f;
     // strips long enough to amortise the two halo rows, short enough to fill 148 SMs x 16 warps
     const long long target_threads = 148LL * 2048;
     int strip = 64;
@@ -625,8 +634,10 @@ int launch_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int
     else if (minb == 6) half_sweep_fast_kernel<6><<<grid, 128, 0, st>>>(P);
     else half_sweep_fast_kernel<4><<<grid, 128, 0, st>>>(P);
     if (need_rim) {
-      const long long per_rep = (long long)(rb + rows - re) * P.g.wpr + (wrap_cols ? 0LL : 2LL * frows);
-      half_sweep_rim_kernel<<<blocks_for(per_rep * n_replicas, 128), 128, 0, st>>>(P, rb, re, wrap_cols ? 0 : 1);
+      const int head = (ragged || !wrap_cols) ? 1 : 0;
+      const int tail_begin = ragged ? 4 * nvec_f : (wrap_cols ? P.g.wpr : P.g.wpr - 1);
+      const long long per_rep = (long long)(rb + rows - re) * P.g.wpr + (long long)(head + P.g.wpr - tail_begin) * frows;
+      half_sweep_rim_kernel<<<blocks_for(per_rep * n_replicas, 128), 128, 0, st>>>(P, rb, re, head, tail_begin);
     }
   } else {
     P.strip_rows = 1;

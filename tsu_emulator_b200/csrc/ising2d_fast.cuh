@@ -75,6 +75,7 @@ struct SweepParams {
   int strip_rows;  // rows per thread strip (fast path)
   int n_strips;    // strips per replica (fast path)
   int row_begin, row_end;  // local rows the fast path updates (rows without a north / south neighbour are left to the rim pass)
+  int nvec_fast;           // 4-word groups per row the fast path updates (all their lanes exist); the rest is rim
   int debug_flags; // experiments only (TSU_LATTICE_DEBUG): bit0 = skip tie resolution (WRONG results)
 };
 
@@ -171,7 +172,7 @@ __device__ __forceinline__ void drain_tie_queue(const TieQueue& tp, uint32_t lan
 __device__ __forceinline__ void half_sweep_fast_body(const SweepParams& P) {
   __shared__ TieQueue tie_queues[4][2];
   const Geom& g = P.g;
-  const int nvec = g.wpr >> 2;
+  const int nvec = P.nvec_fast;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int per_rep = P.n_strips * nvec;
   const int per_rep_pad = (per_rep + 31) & ~31;

@@ -151,7 +151,7 @@ class Ising2DEngine:
 
         if os.environ.get("TSU_B200_NO_JIT"):
             return False
-        wide = self.cols % 256 == 0 and self.rows >= 3
+        wide = (self.cols // 2) // 32 >= 4 and self.rows >= 3   # at least one 4-word group of full words per row
         if not wide:
             return False  # only the wide full-word kernel has a specialised form (open rims run the generic kernel)
         if force or os.environ.get("TSU_B200_JIT"):
