@@ -85,12 +85,25 @@ def _site_words(rows, cols, colour, row0=0):
     return i, j, mask, k >> 5, k & 31
 
 
+def lattice_counter(w, colour, kind, row_global):
+    """Philox counter words 0 and 1 of a lattice call (words 2, 3 are sweep and replica): everything that varies
+    along a thread's walk down its rows (row, word within its 4-word group, kind) sits in word 1.  Rows < 2^24."""
+    w = np.asarray(w).astype(np.uint64)
+    c0 = (w >> np.uint64(2)) | np.uint64(colour << 24)
+    c1 = (
+        np.asarray(row_global).astype(np.uint64)
+        | ((w & np.uint64(3)) << np.uint64(24))
+        | (np.asarray(kind).astype(np.uint64) << np.uint64(26))
+    )
+    return c0, c1
+
+
 def lattice_uniforms_u32(seed: int, replica: int, sweep: int, colour: int, rows: int, cols: int, row0: int = 0):
     """32-bit uniform of every site of `colour` for sweep index `sweep`.
 
     Frozen definition (shared by the CUDA kernel):
       word w of (row i, colour c) owns compressed sites k in [32w, 32w+32), lane b = k & 31
-      counter = (w | c<<20 | kind<<21,  i_global,  sweep,  replica),  key = (seed_lo, seed_hi)
+      counter = ((w>>2) | c<<24,  i_global | (w&3)<<24 | kind<<26,  sweep,  replica),  key = (seed_lo, seed_hi)
       bit (31-p) of u, p in 0..7  = bit b of output word (p & 3) of call kind (p >> 2)
       low 24 bits of u            = output word (b & 3) of call kind 8 + (b >> 2), shifted right by 8
     Returns u32[rows, cols] (uint32; entries of the other colour are 0) and the colour mask.
@@ -101,18 +114,14 @@ def lattice_uniforms_u32(seed: int, replica: int, sweep: int, colour: int, rows:
     i_b, w_b, b_b = np.broadcast_arrays(i, w, b)
     u = np.zeros((rows, cols), dtype=np.uint64)
     for call in range(2):
-        c0 = w_b.astype(np.uint64) | np.uint64(colour << 20) | np.uint64((KIND_PLANE0 + call) << 21)
-        out = philox4x32_10(c0, i_b, sweep & 0xFFFFFFFF, replica, k0, k1)
+        c0, c1 = lattice_counter(w_b, colour, KIND_PLANE0 + call, i_b)
+        out = philox4x32_10(c0, c1, sweep & 0xFFFFFFFF, replica, k0, k1)
         for q in range(4):
             p = call * 4 + q
             bit = (out[q].astype(np.uint64) >> b_b.astype(np.uint64)) & np.uint64(1)
             u |= bit << np.uint64(31 - p)
-    c0 = (
-        w_b.astype(np.uint64)
-        | np.uint64(colour << 20)
-        | ((np.uint64(KIND_LOW0) + (b_b.astype(np.uint64) >> np.uint64(2))) << np.uint64(21))
-    )
-    out = philox4x32_10(c0, i_b, sweep & 0xFFFFFFFF, replica, k0, k1)
+    c0, c1 = lattice_counter(w_b, colour, np.uint64(KIND_LOW0) + (b_b.astype(np.uint64) >> np.uint64(2)), i_b)
+    out = philox4x32_10(c0, c1, sweep & 0xFFFFFFFF, replica, k0, k1)
     sel = b_b & 3
     low = np.choose(sel, [o.astype(np.uint64) for o in out]) >> np.uint64(8)
     u |= low
@@ -128,8 +137,8 @@ def init_bits(seed: int, replica: int, rows: int, cols: int, row0: int = 0) -> n
     for colour in range(2):
         i, j, mask, w, b = _site_words(rows, cols, colour, row0)
         i_b, w_b, b_b = np.broadcast_arrays(i, w, b)
-        c0 = w_b.astype(np.uint64) | np.uint64(colour << 20) | np.uint64(KIND_INIT << 21)
-        out = philox4x32_10(c0, i_b, 0, replica, k0, k1)
+        c0, c1 = lattice_counter(w_b, colour, KIND_INIT, i_b)
+        out = philox4x32_10(c0, c1, 0, replica, k0, k1)
         bit = (out[0].astype(np.uint64) >> b_b.astype(np.uint64)) & np.uint64(1)
         bits = np.where(mask, bit.astype(np.int64), bits)
     return bits

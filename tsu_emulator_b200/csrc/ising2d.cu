@@ -120,11 +120,11 @@ __device__ __forceinline__ uint32_t bitsel(uint32_t m, uint32_t a, uint32_t b) {
   return (m & a) | (~m & b);
 }
 
-__device__ __forceinline__ uint32_t lane_uniform(const uint32_t r[8], const Coords& q, int j) {
+__device__ __forceinline__ uint32_t lane_uniform(const uint32_t r[8], const Coords& q, uint32_t w, uint32_t row_g, int j) {
   uint32_t u = 0;
 #pragma unroll
   for (int k = 0; k < 8; ++k) u |= ((r[k] >> j) & 1u) << (31 - k);
-  tsu_u32x4 lo = lattice_call(q, TSU_KIND_LOW0 + (uint32_t)(j >> 2));
+  tsu_u32x4 lo = lattice_call(q, w, row_g, TSU_KIND_LOW0 + (uint32_t)(j >> 2));
   int sel = j & 3;
   uint32_t v = sel == 0 ? lo.x : (sel == 1 ? lo.y : (sel == 2 ? lo.z : lo.w));
   return u | (v >> 8);
@@ -142,7 +142,8 @@ __device__ __forceinline__ uint32_t lane_accept(const uint32_t* __restrict__ lut
 template <bool FAST>
 __device__ __forceinline__ uint32_t update_word(uint32_t a, uint32_t b, uint32_t c, uint32_t s, const LutRegs& L,
                                                 const uint32_t* __restrict__ lut, int d_row, uint32_t valid,
-                                                uint32_t missW, uint32_t missE, const Coords& q) {
+                                                uint32_t missW, uint32_t missE, const Coords& q, uint32_t w,
+                                                uint32_t row_g) {
   // bit-sliced count of up neighbours: c2 c1 c0
   const uint32_t s1 = a ^ b ^ c;
   const uint32_t m1 = tsu_lop3_maj(a, b, c);
@@ -153,8 +154,8 @@ __device__ __forceinline__ uint32_t update_word(uint32_t a, uint32_t b, uint32_t
 
   uint32_t r[8];
   {
-    tsu_u32x4 p0 = lattice_call(q, TSU_KIND_PLANE0);
-    tsu_u32x4 p1 = lattice_call(q, TSU_KIND_PLANE1);
+    tsu_u32x4 p0 = lattice_call(q, w, row_g, TSU_KIND_PLANE0);
+    tsu_u32x4 p1 = lattice_call(q, w, row_g, TSU_KIND_PLANE1);
     r[0] = p0.x; r[1] = p0.y; r[2] = p0.z; r[3] = p0.w;
     r[4] = p1.x; r[5] = p1.y; r[6] = p1.z; r[7] = p1.w;
   }
@@ -187,7 +188,7 @@ __device__ __forceinline__ uint32_t update_word(uint32_t a, uint32_t b, uint32_t
     const int j = __ffs(eq) - 1;
     eq &= eq - 1u;
     const int up = ((c0 >> j) & 1u) | (((c1 >> j) & 1u) << 1) | (((c2 >> j) & 1u) << 2);
-    const uint32_t bit = lane_accept(lut, d_row, up, lane_uniform(r, q, j));
+    const uint32_t bit = lane_accept(lut, d_row, up, lane_uniform(r, q, w, row_g, j));
     lt = (lt & ~(1u << j)) | (bit << j);
   }
   if (!FAST) {
@@ -196,7 +197,7 @@ __device__ __forceinline__ uint32_t update_word(uint32_t a, uint32_t b, uint32_t
       special &= special - 1u;
       const int up = ((c0 >> j) & 1u) | (((c1 >> j) & 1u) << 1) | (((c2 >> j) & 1u) << 2);
       const int d = d_row - (int)((missW >> j) & 1u) - (int)((missE >> j) & 1u);
-      const uint32_t bit = lane_accept(lut, d, up, lane_uniform(r, q, j));
+      const uint32_t bit = lane_accept(lut, d, up, lane_uniform(r, q, w, row_g, j));
       lt = (lt & ~(1u << j)) | (bit << j);
     }
     lt &= valid;
@@ -204,9 +205,9 @@ __device__ __forceinline__ uint32_t update_word(uint32_t a, uint32_t b, uint32_t
   return lt;
 }
 
-template <int MINB>
+template <int W, int MINB>
 __global__ void __launch_bounds__(128, MINB) half_sweep_fast_kernel(SweepParams P) {
-  tsu_fast::half_sweep_fast_body(P);
+  tsu_fast::half_sweep_fast_body<W>(P);
 }
 
 // One word of (replica rep, colour, local row i): any size, open or periodic edges, ragged last word.
@@ -226,13 +227,13 @@ __device__ __forceinline__ void generic_update_one(const SweepParams& P, int col
   LutRegs L;
   load_lut_regs(L, lut, d_row);
   Coords q;
-  q.c0_base = (uint32_t)w | ((uint32_t)colour << 20);
-  q.row_g = (uint32_t)(g.row0 + i);
+  q.colour = (uint32_t)colour;
   q.sweep = sweep;
   q.replica = P.replica0 + (uint32_t)rep;
   q.k0 = P.k0;
   q.k1 = P.k1;
-  own[(size_t)i * g.wpr + w] = update_word<false>(h.n, h.s, h.c, h.side, L, lut, d_row, h.valid, h.missW, h.missE, q);
+  own[(size_t)i * g.wpr + w] = update_word<false>(h.n, h.s, h.c, h.side, L, lut, d_row, h.valid, h.missW, h.missE, q,
+                                                  (uint32_t)w, (uint32_t)(g.row0 + i));
 }
 
 // Generic path: one thread per word, one launch per half-sweep.
@@ -341,8 +342,8 @@ __global__ void init_random_kernel(uint32_t* state, Geom g, uint32_t replica0, u
   const int w = (int)(rem - (long long)i * g.wpr);
   const int p = (g.row0 + i + colour) & 1;
   const uint32_t valid = lane_mask_lt(colour_count(g.cols, p) - 32 * w);
-  tsu_u32x4 o = tsu_philox4x32_10(TSU_LATTICE_C0(w, colour, TSU_KIND_INIT), (uint32_t)(g.row0 + i), 0u,
-                                  replica0 + (uint32_t)rep, k0, k1);
+  tsu_u32x4 o = tsu_lattice_philox((uint32_t)w, (uint32_t)colour, TSU_KIND_INIT, (uint32_t)(g.row0 + i), 0u,
+                                   replica0 + (uint32_t)rep, k0, k1);
   state[tid] = o.x & valid;
 }
 
@@ -503,8 +504,40 @@ __global__ void energy_from_obs_kernel(const unsigned long long* __restrict__ ob
 }
 
 bool geom_ok(int n_replicas, int rows, int cols) {
-  return n_replicas > 0 && rows > 0 && cols > 0 && cols < (1 << 26) && rows < (1 << 30);
+  // counter word 1 of the lattice stream keeps the global row in 24 bits, counter word 0 the 4-word group in 24
+  return n_replicas > 0 && rows > 0 && cols > 0 && cols < (1 << 26) && rows <= TSU_LATTICE_MAX_ROWS;
 }
+
+bool rows_ok(int rows, int row0) { return row0 >= 0 && (long long)row0 + rows <= TSU_LATTICE_MAX_ROWS; }
+
+// Tuning knobs (never change results), read once per process:
+//   TSU_LATTICE_STRIP  rows per thread strip of the wide kernel (default: 64, shortened until the grid fills the GPU)
+//   TSU_LATTICE_W      words per thread of the prebuilt wide kernel (2 or 4)
+//   TSU_LATTICE_OPEN_GENERIC / TSU_LATTICE_OBS_GENERIC / TSU_LATTICE_RESIDENT=0  force the one-thread-per-word kernels
+//   TSU_JIT_W, TSU_JIT_MINB, TSU_JIT_UNROLL   words per thread, CTAs per SM and row-loop unrolling the run-time
+//                                             specialised kernel is compiled for
+struct Tuning {
+  int strip = 0, w = 0, open_generic = 0, obs_generic = 0, resident = 1, jit_w = 0, jit_minb = 0, jit_unroll = 0;
+  Tuning() {
+    auto num = [](const char* name, int dflt) {
+      const char* e = getenv(name);
+      return e ? atoi(e) : dflt;
+    };
+    strip = num("TSU_LATTICE_STRIP", 0);
+    w = num("TSU_LATTICE_W", 0);
+    open_generic = getenv("TSU_LATTICE_OPEN_GENERIC") != nullptr;
+    obs_generic = getenv("TSU_LATTICE_OBS_GENERIC") != nullptr;
+    resident = num("TSU_LATTICE_RESIDENT", 1);
+    jit_w = num("TSU_JIT_W", 0);
+    jit_minb = num("TSU_JIT_MINB", 0);
+    jit_unroll = num("TSU_JIT_UNROLL", 0);
+  }
+};
+const Tuning& tuning() {
+  static const Tuning t;
+  return t;
+}
+constexpr int kDefaultW = 4, kDefaultJitW = 4, kDefaultJitMinB = 4;
 
 Geom make_geom(int n_replicas, int rows, int cols, int wrap_rows, int wrap_cols, int row0) {
   Geom g;
@@ -541,7 +574,11 @@ struct JitApi {
 JitApi g_jit;
 std::mutex g_jit_mutex;
 std::map<std::string, int> g_jit_cache;  // "device:t0,..,t7" -> handle
-std::vector<void*> g_jit_functions;      // handle - 1 -> CUfunction
+struct JitKernel {
+  void* fn;
+  int w;  // words per thread it was compiled for
+};
+std::vector<JitKernel> g_jit_functions;  // handle - 1 -> kernel
 
 template <typename F>
 bool jit_sym(void* lib, const char* name, F& fn) {
@@ -569,16 +606,16 @@ bool jit_load_api() {
   return ok;
 }
 
-void* jit_function(int handle) {
+JitKernel jit_function(int handle) {
   std::lock_guard<std::mutex> lock(g_jit_mutex);
-  if (handle < 1 || handle > (int)g_jit_functions.size()) return nullptr;
+  if (handle < 1 || handle > (int)g_jit_functions.size()) return JitKernel{nullptr, 0};
   return g_jit_functions[handle - 1];
 }
 
 int launch_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows, int wrap_cols, int colour,
                       const uint32_t* d_lut, const int32_t* d_lut_index, uint64_t seed, uint32_t sweep,
                       uint32_t replica0, int row0, const uint32_t* d_halo_top, const uint32_t* d_halo_bot,
-                      cudaStream_t st, void* jit_fn = nullptr) {
+                      cudaStream_t st, JitKernel jit = JitKernel{nullptr, 0}) {
   SweepParams P;
   P.state = d_state;
   P.lut = d_lut;
@@ -591,11 +628,10 @@ int launch_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int
   P.replica0 = replica0;
   P.k0 = (uint32_t)seed;
   P.k1 = (uint32_t)(seed >> 32);
+  P.keys = tsu_philox_key_schedule(P.k0, P.k1);
   P.row_begin = 0;
   P.row_end = rows;
   P.nvec_fast = P.g.wpr / 4;
-  P.debug_flags = 0;
-  if (const char* e = getenv("TSU_LATTICE_DEBUG")) P.debug_flags = atoi(e);
   // rows that have a north / south neighbour (exactly the cases opp_row() resolves): the wide kernel takes those,
   // columns treated as periodic; what that gets wrong on open lattices is redone by the rim pass
   const bool north_ok = d_halo_top || wrap_rows, south_ok = d_halo_bot || wrap_rows;
@@ -606,33 +642,34 @@ int launch_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int
   const int nvec_f = ragged ? full_words / 4 : P.g.wpr / 4;
   const bool need_rim = rb > 0 || re < rows || !wrap_cols || ragged;
   bool fast = nvec_f >= 1 && re - rb >= 1;
-  if (need_rim && getenv("TSU_LATTICE_OPEN_GENERIC")) fast = false;
+  if (need_rim && tuning().open_generic) fast = false;
   if (fast) {
-    const int nvec = nvec_f;
+    const bool use_jit = jit.fn && !d_lut_index;
+    const int W = use_jit ? jit.w : (tuning().w == 2 ? 2 : kDefaultW);
+    const int nvec = nvec_f * (4 / W);  // W-word groups per row
     const int frows = re - rb;
     P.nvec_fast = nvec_f;
     // strips long enough to amortise the two halo rows, short enough to fill 148 SMs x 16 warps
     const long long target_threads = 148LL * 2048;
     int strip = 64;
     while (strip > 1 && (long long)n_replicas * nvec * ((frows + strip - 1) / strip) < target_threads) strip >>= 1;
-    if (const char* e = getenv("TSU_LATTICE_STRIP")) strip = atoi(e) > 0 ? atoi(e) : strip;
+    if (tuning().strip > 0) strip = tuning().strip;
     P.strip_rows = strip;
     P.n_strips = (frows + strip - 1) / strip;
     P.row_begin = rb;
     P.row_end = re;
     const long long per_rep_pad = ((long long)P.n_strips * nvec + 31) / 32 * 32;  // warps never straddle replicas
     const long long total = (long long)n_replicas * per_rep_pad;
-    int minb = 4;
-    if (const char* e = getenv("TSU_LATTICE_MINB")) minb = atoi(e);
     const unsigned grid = blocks_for(total, 128);
-    if (jit_fn && !d_lut_index) {  // table-specialised build of the same kernel body
+    if (use_jit) {  // table-specialised build of the same kernel body
       void* args[] = {&P};
-      int rc = g_jit.cuLaunchKernel(jit_fn, grid, 1, 1, 128, 1, 1, 0, (void*)st, args, nullptr);
+      int rc = g_jit.cuLaunchKernel(jit.fn, grid, 1, 1, 128, 1, 1, 0, (void*)st, args, nullptr);
       if (rc != 0) return 999;  // CUDA_ERROR_UNKNOWN for a driver-API launch failure
-    } else if (minb == 3) half_sweep_fast_kernel<3><<<grid, 128, 0, st>>>(P);
-    else if (minb == 5) half_sweep_fast_kernel<5><<<grid, 128, 0, st>>>(P);
-    else if (minb == 6) half_sweep_fast_kernel<6><<<grid, 128, 0, st>>>(P);
-    else half_sweep_fast_kernel<4><<<grid, 128, 0, st>>>(P);
+    } else if (W == 2) {
+      half_sweep_fast_kernel<2, 8><<<grid, 128, 0, st>>>(P);
+    } else {
+      half_sweep_fast_kernel<4, 4><<<grid, 128, 0, st>>>(P);
+    }
     if (need_rim) {
       const int head = (ragged || !wrap_cols) ? 1 : 0;
       const int tail_begin = ragged ? 4 * nvec_f : (wrap_cols ? P.g.wpr : P.g.wpr - 1);
@@ -651,9 +688,7 @@ int launch_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int
 
 // true when a replica is small enough that per-half-sweep launches would be pure launch latency
 bool resident_eligible(int n_replicas, int rows, int cols) {
-  if (const char* e = getenv("TSU_LATTICE_RESIDENT")) {
-    if (atoi(e) == 0) return false;
-  }
+  if (tuning().resident == 0) return false;
   const long long per_rep = (long long)rows * words_per_row(cols);
   // <= 16 words per thread and half-sweep, and not enough replicas to fill the GPU with the wide kernels
   return per_rep <= 16LL * kResidentThreads && (long long)n_replicas * per_rep <= 148LL * 2048;
@@ -690,7 +725,7 @@ int64_t tsu_ising2d_state_words(int rows, int cols) {
 
 int tsu_ising2d_init_random(uint32_t* d_state, int n_replicas, int rows, int cols, uint64_t seed, uint32_t replica0,
                             int row0, uintptr_t stream) {
-  TSU_CHECK_ARG(d_state && geom_ok(n_replicas, rows, cols) && row0 >= 0);
+  TSU_CHECK_ARG(d_state && geom_ok(n_replicas, rows, cols) && rows_ok(rows, row0));
   Geom g = make_geom(n_replicas, rows, cols, 0, 0, row0);
   const long long total = 2LL * rows * g.wpr * n_replicas;
   init_random_kernel<<<blocks_for(total, 256), 256, 0, tsu_stream(stream)>>>(d_state, g, replica0, (uint32_t)seed,
@@ -719,7 +754,7 @@ int tsu_ising2d_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols
                            int colour, const uint32_t* d_lut, const int32_t* d_lut_index, uint64_t seed,
                            uint32_t sweep, uint32_t replica0, int row0, const uint32_t* d_halo_top,
                            const uint32_t* d_halo_bot, uintptr_t stream) {
-  TSU_CHECK_ARG(d_state && d_lut && geom_ok(n_replicas, rows, cols) && row0 >= 0);
+  TSU_CHECK_ARG(d_state && d_lut && geom_ok(n_replicas, rows, cols) && rows_ok(rows, row0));
   TSU_CHECK_ARG(colour == 0 || colour == 1);
   TSU_CHECK_ARG(!wrap_cols || (cols % 2 == 0 && cols > 2));
   TSU_CHECK_ARG(!wrap_rows || (rows % 2 == 0 && rows > 2) || d_halo_top || d_halo_bot);
@@ -750,7 +785,7 @@ int tsu_ising2d_half_sweep_injected(uint32_t* d_state, int n_replicas, int rows,
                                     int wrap_cols, int colour, const uint32_t* d_lut, const int32_t* d_lut_index,
                                     const uint32_t* d_uniforms, int row0, const uint32_t* d_halo_top,
                                     const uint32_t* d_halo_bot, uintptr_t stream) {
-  TSU_CHECK_ARG(d_state && d_lut && d_uniforms && geom_ok(n_replicas, rows, cols) && row0 >= 0);
+  TSU_CHECK_ARG(d_state && d_lut && d_uniforms && geom_ok(n_replicas, rows, cols) && rows_ok(rows, row0));
   TSU_CHECK_ARG(colour == 0 || colour == 1);
   TSU_CHECK_ARG(!wrap_cols || (cols % 2 == 0 && cols > 2));
   TSU_CHECK_ARG(!wrap_rows || (rows % 2 == 0 && rows > 2) || d_halo_top || d_halo_bot);
@@ -765,7 +800,6 @@ int tsu_ising2d_half_sweep_injected(uint32_t* d_state, int n_replicas, int rows,
   P.sweep = 0;
   P.replica0 = 0;
   P.k0 = P.k1 = 0;
-  P.debug_flags = 0;
   P.strip_rows = 1;
   P.n_strips = rows;
   const long long total = (long long)n_replicas * rows * P.g.wpr;
@@ -775,13 +809,12 @@ int tsu_ising2d_half_sweep_injected(uint32_t* d_state, int n_replicas, int rows,
 
 int tsu_ising2d_observables(const uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows, int wrap_cols,
                             int row0, const uint32_t* d_next_rows, unsigned long long* d_out, uintptr_t stream) {
-  TSU_CHECK_ARG(d_state && d_out && geom_ok(n_replicas, rows, cols) && row0 >= 0);
-  TSU_CHECK_ARG(n_replicas <= 65535);
+  TSU_CHECK_ARG(d_state && d_out && geom_ok(n_replicas, rows, cols) && rows_ok(rows, row0));
   Geom g = make_geom(n_replicas, rows, cols, wrap_rows, wrap_cols, row0);
   cudaStream_t st = tsu_stream(stream);
   cudaError_t e = cudaMemsetAsync(d_out, 0, sizeof(unsigned long long) * 2 * (size_t)n_replicas, st);
   if (e != cudaSuccess) return (int)e;
-  if (cols % 256 == 0 && !getenv("TSU_LATTICE_OBS_GENERIC")) {
+  if (cols % 256 == 0 && !tuning().obs_generic) {
     const int nvec = g.wpr / 4;
     int strip = 64;  // long strips re-read one row in `strip`; short ones fill the GPU for small batches
     while (strip > 1 && (long long)n_replicas * nvec * ((rows + strip - 1) / strip) < 148LL * 2048) strip >>= 1;
@@ -791,6 +824,7 @@ int tsu_ising2d_observables(const uint32_t* d_state, int n_replicas, int rows, i
                                                                                                 strip, n_strips, d_out);
     TSU_RETURN_LAUNCH_STATUS();
   }
+  TSU_CHECK_ARG(n_replicas <= 65535);  // gridDim.y of the word-by-word kernel
   const long long n_words = 2LL * rows * g.wpr;
   long long bx = (n_words + 255) / 256;
   const long long cap = (148LL * 8 + n_replicas - 1) / n_replicas;  // about 8 CTAs per SM in total
@@ -829,21 +863,23 @@ int tsu_ising2d_jit_prepare(const uint32_t* h_lut, const char* src_dir, char* lo
   for (int u = 0; u < 5; ++u)
     if ((h_lut[20 + u] & 0x00ffffffu) == 0u && !((h_lut[25] >> (20 + u)) & 1u)) fz |= 1u << u;
   char key[160];
-  snprintf(key, sizeof key, "%d:%u,%u,%u,%u,%u,%u,%u,%u;%u", dev, tab[0], tab[1], tab[2], tab[3], tab[4], tab[5], tab[6],
-           tab[7], fz);
+  snprintf(key, sizeof key, "%d:%u,%u,%u,%u,%u,%u,%u,%u;%u;%u", dev, tab[0], tab[1], tab[2], tab[3], tab[4], tab[5], tab[6],
+           tab[7], fz, (h_lut[25] >> 20) & 31u);
   auto it = g_jit_cache.find(key);
   if (it != g_jit_cache.end()) return it->second;
   std::string src;
   for (int k = 0; k < 8; ++k) src += "#define TSU_FT" + std::to_string(k) + " " + std::to_string(tab[k]) + "\n";
   src += "#define TSU_FZ " + std::to_string(fz) + "\n";
-  int minb = 4;
-  if (const char* e = getenv("TSU_JIT_MINB")) minb = atoi(e) > 0 ? atoi(e) : 4;
+  const int jw = tuning().jit_w == 2 ? 2 : (tuning().jit_w == 4 ? 4 : kDefaultJitW);
+  const int minb = tuning().jit_minb > 0 ? tuning().jit_minb : (jw == 2 ? 2 * kDefaultJitMinB : kDefaultJitMinB);
+  src += "#define TSU_ALWAYS " + std::to_string((h_lut[25] >> 20) & 31u) + "u\n";
   src += "#define TSU_JIT_MINB " + std::to_string(minb) + "\n";
-  if (getenv("TSU_JIT_WIDE")) src += "#define TSU_JIT_WIDE 1\n";
+  src += "#define TSU_JIT_W " + std::to_string(jw) + "\n";
+  if (tuning().jit_unroll > 1) src += "#define TSU_ROW_UNROLL " + std::to_string(tuning().jit_unroll) + "\n";
   src +=
       "#include \"ising2d_fast.cuh\"\n"
       "extern \"C\" __global__ void __launch_bounds__(128, TSU_JIT_MINB) tsu_jit_half_sweep(tsu_fast::SweepParams P) {\n"
-      "  tsu_fast::half_sweep_fast_body(P);\n}\n";
+      "  tsu_fast::half_sweep_fast_body<TSU_JIT_W>(P);\n}\n";
   void* prog = nullptr;
   if (g_jit.nvrtcCreateProgram(&prog, src.c_str(), "tsu_jit.cu", 0, nullptr, nullptr) != 0) return 0;
   const std::string inc = std::string("-I") + src_dir;
@@ -871,7 +907,7 @@ int tsu_ising2d_jit_prepare(const uint32_t* h_lut, const char* src_dir, char* lo
     g_jit_cache[key] = 0;
     return 0;
   }
-  g_jit_functions.push_back(fn);
+  g_jit_functions.push_back(JitKernel{fn, jw});
   const int handle = (int)g_jit_functions.size();
   g_jit_cache[key] = handle;
   return handle;
@@ -881,7 +917,7 @@ int tsu_ising2d_half_sweep_jit(int jit_handle, uint32_t* d_state, int n_replicas
                                int wrap_cols, int colour, const uint32_t* d_lut, uint64_t seed, uint32_t sweep,
                                uint32_t replica0, int row0, const uint32_t* d_halo_top, const uint32_t* d_halo_bot,
                                uintptr_t stream) {
-  TSU_CHECK_ARG(d_state && d_lut && geom_ok(n_replicas, rows, cols) && row0 >= 0);
+  TSU_CHECK_ARG(d_state && d_lut && geom_ok(n_replicas, rows, cols) && rows_ok(rows, row0));
   TSU_CHECK_ARG(colour == 0 || colour == 1);
   TSU_CHECK_ARG(!wrap_cols || (cols % 2 == 0 && cols > 2));
   TSU_CHECK_ARG(!wrap_rows || (rows % 2 == 0 && rows > 2) || d_halo_top || d_halo_bot);
@@ -898,7 +934,7 @@ int tsu_ising2d_sweeps_jit(int jit_handle, uint32_t* d_state, int n_replicas, in
   if (n_sweeps > 0 && resident_eligible(n_replicas, rows, cols))  // launch latency dominates: one launch for everything
     return launch_resident_sweeps(d_state, n_replicas, rows, cols, wrap_rows, wrap_cols, d_lut, nullptr, seed, sweep0,
                                   n_sweeps, replica0, tsu_stream(stream));
-  void* fn = jit_function(jit_handle);
+  const JitKernel fn = jit_function(jit_handle);
   for (int t = 0; t < n_sweeps; ++t) {
     for (int colour = 0; colour < 2; ++colour) {
       int rc = launch_half_sweep(d_state, n_replicas, rows, cols, wrap_rows, wrap_cols, colour, d_lut, nullptr, seed,
