@@ -48,6 +48,10 @@ void tsu_philox4x32_10_host(const uint32_t ctr[4], const uint32_t key[2], uint32
 int tsu_philox_fill_u32(uint32_t* d_out, uint64_t n, uint64_t seed, uint32_t offset, uintptr_t stream);
 
 /* ------------------------------------------------------------------ 2-D lattice ------- */
+/* The lattice kernels read their tuning knobs (TSU_LATTICE_STRIP, TSU_LATTICE_W, TSU_LATTICE_RESIDENT,
+ * TSU_LATTICE_OPEN_GENERIC, TSU_LATTICE_OBS_GENERIC, TSU_JIT_W, TSU_JIT_MINB, TSU_JIT_UNROLL: launch shapes and
+ * kernel choice, never results) from the environment once, when the library is loaded; this reads them again. */
+void tsu_ising2d_reload_tuning(void);
 /*
  * Replaces the inner loop of GibbsSampler.gibbs_sweep / sample_conditional
  * (tsu/gibbs.py:102-162) for the nearest-neighbour lattice that IsingGrid wires up
@@ -89,6 +93,15 @@ int tsu_ising2d_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols
                            const int32_t* d_lut_index, uint64_t seed, uint32_t sweep,
                            uint32_t replica0, int row0, const uint32_t* d_halo_top,
                            const uint32_t* d_halo_bot, uintptr_t stream);
+/* The same update restricted to the local rows [row_begin, row_end) (the others are neither read for writing nor
+ * written): lets a row-slab driver update its two boundary rows first, send them to the ring neighbours and
+ * update the interior while the halo exchange is in flight.  jit_handle > 0 (and d_lut_index == NULL) selects the
+ * run-time specialised kernel of tsu_ising2d_jit_prepare; bits are identical for any split of the rows. */
+int tsu_ising2d_half_sweep_rows(int jit_handle, uint32_t* d_state, int n_replicas, int rows, int cols,
+                                int wrap_rows, int wrap_cols, int colour, const uint32_t* d_lut,
+                                const int32_t* d_lut_index, uint64_t seed, uint32_t sweep,
+                                uint32_t replica0, int row0, const uint32_t* d_halo_top,
+                                const uint32_t* d_halo_bot, int row_begin, int row_end, uintptr_t stream);
 /* n_sweeps full sweeps (black then white), sweep indices sweep0 .. sweep0+n_sweeps-1, no halos.
  * Two launches per sweep; lattices of at most 4096 words per replica in batches that would not fill the GPU
  * (BASELINE config 1: 50 x 50) run ALL sweeps of the call in ONE launch, one thread block per replica.  Same

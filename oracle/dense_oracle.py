@@ -138,3 +138,25 @@ def philox_uniforms_tc(seed, chain, sweep, N):
                       (seed >> 32) & 0xFFFFFFFF)
     w = np.choose((sites & np.uint64(3)).astype(np.int64), [x.astype(np.uint64) for x in o])
     return (w >> np.uint64(8)).astype(np.float64) / 16777216.0
+
+
+def tc_sweep_disagreements(start, after, coupling, bias, T, uniforms):
+    """One sequential sweep (gibbs.py:153-160) of ONE chain replayed against a kernel's result `after`.
+
+    The replay follows the kernel's own trajectory: at every site the float64 field of the reference
+    (gibbs.py:97-99) is evaluated on the state the kernel had at that moment, the reference's decision
+    `u < sigmoid(h / T)` (gibbs.py:125-126) is compared with the kernel's bit, and the kernel's bit is kept.
+    Returns [(site, |u - p|)] for the sites where the two decisions differ: a reduced-precision kernel may only
+    disagree where the uniform lies within its field / threshold error of the acceptance probability.
+    """
+    cur = np.array(start, dtype=np.float64, copy=True)
+    J = np.asarray(coupling, dtype=np.float64)
+    out = []
+    for i in range(len(cur)):
+        h = float(np.dot(J[i, :], cur)) + (0.0 if bias is None else float(bias[i]))
+        p = sigmoid_ref(h / T)
+        want = 1 if uniforms[i] < p else 0
+        if want != int(after[i]):
+            out.append((i, abs(float(uniforms[i]) - p)))
+        cur[i] = after[i]
+    return out

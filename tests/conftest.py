@@ -35,3 +35,32 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+class _Tuning:
+    """environment knobs of the lattice kernels: the library reads them once, so every change is followed by
+    tsu_ising2d_reload_tuning()"""
+
+    def __init__(self, monkeypatch):
+        self.mp = monkeypatch
+
+    def _reload(self):
+        from tsu_emulator_b200 import _lib
+
+        _lib.load().tsu_ising2d_reload_tuning()
+
+    def setenv(self, name, value):
+        self.mp.setenv(name, value)
+        self._reload()
+
+    def delenv(self, name):
+        self.mp.delenv(name, raising=False)
+        self._reload()
+
+
+@pytest.fixture
+def tuning(monkeypatch):
+    t = _Tuning(monkeypatch)
+    yield t
+    monkeypatch.undo()
+    t._reload()

@@ -45,9 +45,10 @@ class OracleEngine:
         row[p::2] = (w[k >> 5] >> (k & 31).astype(np.uint32)) & 1
         return row
 
-    def half_sweep(self, colour, halo_top=None, halo_bot=None, uniforms=None):
+    def half_sweep(self, colour, halo_top=None, halo_bot=None, uniforms=None, rows=None):
         for r in range(self.n_replicas):
             b = self.bits(r)
+            before = b.copy()
             top = bot = None
             if halo_top is not None:
                 top = self._row_from_words(halo_top[r], self.row0 - 1, 1 - colour)
@@ -60,6 +61,10 @@ class OracleEngine:
             u = O.philox_uniform_field(self.seed, self.replica0 + r, self.sweep_index, self.rows, self.cols, self.row0)
             O.half_sweep_slab(b, top, bot, colour, u, self.coupling, self.field, float(self.temps[r]), self.wrap_cols,
                               self.row0)
+            if rows is not None:  # only the rows [begin, end) are updated (a half-sweep reads the other colour only)
+                keep = np.ones(self.rows, dtype=bool)
+                keep[rows[0]:rows[1]] = False
+                b[keep] = before[keep]
             self.set_bits(r, b)
 
     def sweep(self, n=1):

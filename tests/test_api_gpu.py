@@ -194,3 +194,23 @@ def test_demonstrate_phase_transition_driver():
     for r in res.values():
         assert set(r) == {"temperatures", "magnetizations", "susceptibilities", "specific_heats"}
         assert r["magnetizations"][0] > 0.9 > r["magnetizations"][2]
+
+
+def test_odd_periodic_grid_takes_the_dense_path():
+    """IsingGrid((5, 5), periodic=True): odd rings are not two-colourable, so the grid samples through the dense-J
+    sampler exactly like the reference (ising.py:343-361 wires any size); checked against exact enumeration of a
+    3 x 3 torus and for shape / values on 5 x 5"""
+    from tsu_emulator_b200 import IsingConfig, IsingGrid
+    g = IsingGrid((5, 5), J=1.0, config=IsingConfig(temperature=2.5, n_burnin=20, n_sweeps=2), periodic=True, seed=3)
+    out = g.sample(50)
+    assert out.shape == (50, 25) and set(np.unique(out)) <= {-1, 1}
+    assert g.J[0, 4] == 1.0 and g.J[0, 20] == 1.0          # the wrap bonds exist
+    T = 3.0
+    g3 = IsingGrid((3, 3), J=1.0, config=IsingConfig(temperature=T, n_burnin=50, n_sweeps=3), periodic=True, seed=5)
+    smp = g3.sample(6000)
+    states = np.array([[1 - 2 * ((k >> i) & 1) for i in range(9)] for k in range(512)])
+    E = np.array([g3.energy(s_) for s_ in states])
+    p = np.exp(-E / T); p /= p.sum()
+    e_exact = float((p * E).sum())
+    e_mc = float(np.mean([g3.energy(s_) for s_ in smp]))
+    assert abs(e_mc - e_exact) < 0.35, (e_mc, e_exact)

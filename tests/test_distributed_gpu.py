@@ -80,3 +80,46 @@ def test_lattice_tempering_device_swap_matches_host_pass():
     assert np.array_equal(sr_dev, sr_host) and np.array_equal(m_dev, m_host) and np.array_equal(e_dev, e_host)
     assert stats[0] == 30 * 4 * 4 and 0 < stats[1] <= stats[0]         # 30 passes x 4 ladders x 4 pairs
     assert e_dev.mean(0)[0] < e_dev.mean(0)[-1]                        # colder slots sit at lower energy
+
+
+def _slab_rank(rank, world, port, rows, cols, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from tsu_emulator_b200 import Ising2DEngine
+    from tsu_emulator_b200.distributed import SlabShardedIsing2D
+
+    ok = True
+    for overlap in (True, False):
+        fac = lambda lr, r0: Ising2DEngine(lr, cols, temperature=2.269, periodic=True, seed=7, row0=r0, global_rows=rows).init_random()
+        drv = SlabShardedIsing2D(rows, cols, fac, periodic=True, overlap=overlap).sweep(2).sweep(1)
+        whole = Ising2DEngine(rows, cols, temperature=2.269, periodic=True, seed=7).init_random().sweep(3)
+        lr = rows // world
+        ok = ok and torch.equal(drv.engine.state[0], whole.state[0][:, rank * lr:(rank + 1) * lr, :])
+        ok = ok and torch.equal(drv.observables(), whole.observables_tensor())
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_slabs_on_all_gpus_match_single_gpu():
+    """one NCCL rank per visible GPU (skipped on a one-GPU box): overlapped and serial halo exchange give the bits and
+    the observables of the unsharded lattice"""
+    import torch
+    import torch.multiprocessing as mp
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs at least two GPUs")
+    world = 2 if world < 4 else (4 if world < 8 else 8)
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_slab_rank, args=(r, world, port, 2048, 4096, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=300) for _ in range(world)]
+    [p.join(timeout=60) for p in procs]
+    assert all(ok for _, ok in res), res

@@ -82,8 +82,8 @@ PHILOX_CASES = [
 
 @pytest.mark.parametrize("resident", ["1", "0"])   # one-launch resident kernel / one launch per half-sweep
 @pytest.mark.parametrize("rows,cols,periodic,T,J,h", PHILOX_CASES)
-def test_philox_mode_is_bit_exact_with_oracle(rows, cols, periodic, T, J, h, resident, monkeypatch):
-    monkeypatch.setenv("TSU_LATTICE_RESIDENT", resident)
+def test_philox_mode_is_bit_exact_with_oracle(rows, cols, periodic, T, J, h, resident, tuning):
+    tuning.setenv("TSU_LATTICE_RESIDENT", resident)
     n_rep, n_sweeps, seed = 2, 3, 1234
     eng = make_engine(rows, cols, n_replicas=n_rep, coupling=J, field=h, temperature=T, periodic=periodic,
                       seed=seed, replica0=7)
@@ -114,10 +114,10 @@ def test_philox_and_injected_paths_agree_on_philox_uniforms():
     assert (a.get_spins() == b.get_spins()).all()
 
 
-def test_stragglers_exercised(monkeypatch):
+def test_stragglers_exercised(tuning):
     """thresholds whose top byte ties often: every lane with top-8-bit tie must use the low bits (wide kernel: the
     tie queue; a lattice this small would otherwise take the resident kernel)"""
-    monkeypatch.setenv("TSU_LATTICE_RESIDENT", "0")
+    tuning.setenv("TSU_LATTICE_RESIDENT", "0")
     rows, cols, seed = 64, 1024, 77
     eng = make_engine(rows, cols, temperature=2.269, periodic=True, seed=seed)
     eng.init_random()
@@ -155,7 +155,7 @@ def test_observables_match_oracle():
             assert M[r] == pytest.approx(O.magnetization(bits[r]), abs=1e-12)
 
 
-def test_observables_vector_kernel_equals_generic_kernel(monkeypatch):
+def test_observables_vector_kernel_equals_generic_kernel(tuning):
     """the 16-byte-vector observables kernel (periodic columns, cols % 256 == 0) against the word-by-word kernel, for a
     whole lattice and for a row slab that gets its lower neighbour rows from another rank (next_rows)"""
     import torch
@@ -171,7 +171,7 @@ def test_observables_vector_kernel_equals_generic_kernel(monkeypatch):
     nxt = below.state[:, :, 0, :].contiguous()
     fast = [whole.observables_tensor().clone(), slab.observables_tensor(next_rows=nxt).clone(),
             slab.observables_tensor(next_rows=None).clone()]
-    monkeypatch.setenv("TSU_LATTICE_OBS_GENERIC", "1")
+    tuning.setenv("TSU_LATTICE_OBS_GENERIC", "1")
     slow = [whole.observables_tensor().clone(), slab.observables_tensor(next_rows=nxt).clone(),
             slab.observables_tensor(next_rows=None).clone()]
     for f, g in zip(fast, slow):
@@ -180,22 +180,22 @@ def test_observables_vector_kernel_equals_generic_kernel(monkeypatch):
         assert whole.energy()[r] == pytest.approx(O.energy(bits[r], 1.0, 0.0, True), abs=1e-9)
 
 
-def test_open_lattice_wide_kernel_plus_rim_equals_generic_kernel(monkeypatch):
+def test_open_lattice_wide_kernel_plus_rim_equals_generic_kernel(tuning):
     """open boundaries (the IsingGrid default) on full-word lattices: wide kernel for the rows with both vertical
     neighbours + rim pass with the true geometry == the word-by-word generic kernel == the oracle; also for a row slab
     that has a neighbour slab on one side only"""
     import torch
-    monkeypatch.setenv("TSU_LATTICE_RESIDENT", "0")
+    tuning.setenv("TSU_LATTICE_RESIDENT", "0")
     seed = 5
     for rows, cols, periodic in ((66, 1024, False), (40, 1000, True), (33, 1379, False)):
         kw = dict(n_replicas=3, temperature=2.269, periodic=periodic, seed=seed, field=0.1)
         a = make_engine(rows, cols, **kw).init_random()
         start = a.get_spins(pm1=False)
         a.sweep(4)
-        monkeypatch.setenv("TSU_LATTICE_OPEN_GENERIC", "1")
+        tuning.setenv("TSU_LATTICE_OPEN_GENERIC", "1")
         b = make_engine(rows, cols, **kw).init_random()
         b.sweep(4)
-        monkeypatch.delenv("TSU_LATTICE_OPEN_GENERIC")
+        tuning.delenv("TSU_LATTICE_OPEN_GENERIC")
         assert torch.equal(a.state, b.state), (rows, cols, periodic)
         want = O.checkerboard_sweeps_philox(start[2], seed, 2, 0, 4, 1.0, 0.1, 2.269, periodic)
         assert (a.get_spins(pm1=False)[2] == want).all(), (rows, cols, periodic)
@@ -206,7 +206,7 @@ def test_open_lattice_wide_kernel_plus_rim_equals_generic_kernel(monkeypatch):
     top = a.state[:, :, 40, :].contiguous()
     for generic in ("", "1"):
         if generic:
-            monkeypatch.setenv("TSU_LATTICE_OPEN_GENERIC", "1")
+            tuning.setenv("TSU_LATTICE_OPEN_GENERIC", "1")
         slab = make_engine(25, cols, n_replicas=3, temperature=2.269, periodic=False, seed=seed, row0=41, global_rows=rows)
         slab.state.copy_(a.state[:, :, 41:66, :])
         for colour in (0, 1):
@@ -317,7 +317,7 @@ def test_binder_cumulant_crossing_at_tc():
 
 
 @pytest.mark.parametrize("rows,cols,periodic", [(50, 50, True), (50, 50, False), (37, 61, False), (256, 256, True)])
-def test_resident_small_lattice_kernel_matches_per_half_sweep_launches(rows, cols, periodic, monkeypatch):
+def test_resident_small_lattice_kernel_matches_per_half_sweep_launches(rows, cols, periodic, tuning):
     """C1-sized lattices run all sweeps of a call in ONE launch (one thread block per replica); the bits must equal
     the launch-per-half-sweep path (TSU_LATTICE_RESIDENT=0) and the oracle"""
     kw = dict(n_replicas=3, temperature=2.5, periodic=periodic, seed=77)
@@ -325,7 +325,7 @@ def test_resident_small_lattice_kernel_matches_per_half_sweep_launches(rows, col
     a.init_random()
     start = a.get_spins(pm1=False)
     a.sweep(7)
-    monkeypatch.setenv("TSU_LATTICE_RESIDENT", "0")
+    tuning.setenv("TSU_LATTICE_RESIDENT", "0")
     b = make_engine(rows, cols, **kw)
     b.init_random()
     b.sweep(7)
@@ -333,3 +333,46 @@ def test_resident_small_lattice_kernel_matches_per_half_sweep_launches(rows, col
     assert (got == b.get_spins(pm1=False)).all()
     want = O.checkerboard_sweeps_philox(start[1], 77, 1, 0, 7, 1.0, 0.0, 2.5, periodic)
     assert (got[1] == want).all()
+
+
+@pytest.mark.parametrize("rows,cols,periodic", [(40, 1024, True), (33, 1000, False), (24, 512, False), (12, 70, True),
+                                                (9, 50, False)])
+def test_row_ranges_compose_to_the_full_half_sweep(rows, cols, periodic, tuning):
+    """tsu_ising2d_half_sweep_rows: boundary rows, interior and arbitrary splits, launched in any order, give the bits
+    of the one-launch half-sweep (what the overlapped row-slab driver relies on)"""
+    import torch
+    tuning.setenv("TSU_LATTICE_RESIDENT", "0")
+    kw = dict(n_replicas=2, temperature=2.269, periodic=periodic, seed=19, field=0.05)
+    a = make_engine(rows, cols, **kw).init_random()
+    b = make_engine(rows, cols, **kw).init_random()
+    splits = [[(rows - 1, rows), (0, 1), (1, rows - 1)], [(0, rows // 3), (rows // 3, rows)], [(5, rows), (0, 5)]]
+    for t in range(3):
+        for colour in (0, 1):
+            a.half_sweep(colour)
+            for rng_ in splits[t]:
+                b.half_sweep(colour, rows=rng_)
+            assert torch.equal(a.state, b.state), (t, colour)
+        a.sweep_index += 1
+        b.sweep_index += 1
+    want = O.checkerboard_sweeps_philox(O.init_bits(19, 1, rows, cols), 19, 1, 0, 3, 1.0, 0.05, 2.269, periodic)
+    assert (b.get_spins(pm1=False)[1] == want).all()
+
+
+def test_two_word_threads_equal_four_word_threads(tuning, monkeypatch):
+    """W = 2 (64 spins per thread) and W = 4 (128) builds of the wide kernel, prebuilt and run-time specialised"""
+    import torch
+    tuning.setenv("TSU_LATTICE_RESIDENT", "0")
+    rows, cols, seed = 130, 1536, 3
+    ref = make_engine(rows, cols, n_replicas=2, temperature=2.269, periodic=True, seed=seed).init_random().sweep(4)
+    tuning.setenv("TSU_LATTICE_W", "2")
+    w2 = make_engine(rows, cols, n_replicas=2, temperature=2.269, periodic=True, seed=seed).init_random().sweep(4)
+    assert torch.equal(ref.state, w2.state)
+    tuning.setenv("TSU_JIT_W", "2")
+    j2 = make_engine(rows, cols, n_replicas=2, temperature=2.3, periodic=True, seed=seed)   # a temperature no other test compiles
+    if j2.specialise():
+        tuning.delenv("TSU_LATTICE_W")
+        want = make_engine(rows, cols, n_replicas=2, temperature=2.3, periodic=True, seed=seed).init_random().sweep(4)
+        monkeypatch.setenv("TSU_B200_NO_JIT", "1")
+        assert want._jit == 0
+        j2.init_random().sweep(4)
+        assert torch.equal(j2.state, want.state)

@@ -35,6 +35,7 @@ SIGNATURES = {
     "tsu_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "tsu_philox4x32_10_host": (None, [POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint32)]),
     "tsu_philox_fill_u32": (c_int, [c_void_p, c_uint64, c_uint64, c_uint32, c_uintptr]),
+    "tsu_ising2d_reload_tuning": (None, []),
     "tsu_ising2d_words_per_row": (c_int64, [c_int]),
     "tsu_ising2d_state_words": (c_int64, [c_int, c_int]),
     "tsu_ising2d_init_random": (c_int, [c_void_p, c_int, c_int, c_int, c_uint64, c_uint32, c_int, c_uintptr]),
@@ -44,6 +45,11 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_int,
          c_void_p, c_void_p, c_uintptr],
+    ),
+    "tsu_ising2d_half_sweep_rows": (
+        c_int,
+        [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_uint64, c_uint32, c_uint32,
+         c_int, c_void_p, c_void_p, c_int, c_int, c_uintptr],
     ),
     "tsu_ising2d_sweeps": (
         c_int,

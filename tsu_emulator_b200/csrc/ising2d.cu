@@ -238,14 +238,15 @@ __device__ __forceinline__ void generic_update_one(const SweepParams& P, int col
 
 // Generic path: one thread per word, one launch per half-sweep.
 __global__ void __launch_bounds__(128) half_sweep_generic_kernel(SweepParams P) {
+  // rows [P.row_begin, P.row_end) of every replica
   const Geom& g = P.g;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long per_rep = (long long)g.rows * g.wpr;
+  const long long per_rep = (long long)(P.row_end - P.row_begin) * g.wpr;
   if (tid >= per_rep * g.n_replicas) return;
   const int rep = (int)(tid / per_rep);
   const int rem = (int)(tid - (long long)rep * per_rep);
   const int i = rem / g.wpr;
-  generic_update_one(P, P.colour, P.sweep, rep, i, rem - i * g.wpr);
+  generic_update_one(P, P.colour, P.sweep, rep, P.row_begin + i, rem - i * g.wpr);
 }
 
 // Small lattices (C1: 50 x 50): the whole replica belongs to ONE thread block, which runs both colours of
@@ -272,12 +273,19 @@ __global__ void __launch_bounds__(kResidentThreads) sweeps_resident_kernel(Sweep
 // 4-word groups whose lanes all exist, as if the columns wrapped at a word boundary; this pass then recomputes, with the true geometry and degree tables, the rim it
 // got wrong or skipped: rows [0, rb) and [re, rows) completely and, for open columns, the first and last word of the
 // rows in between.  Both passes read only the other colour, so the order of the two launches is the only dependency.
-__global__ void __launch_bounds__(128) half_sweep_rim_kernel(SweepParams P, int rb, int re, int head, int tail_begin) {
-  // rim of a row in [rb, re): word 0 if `head`, and the words tail_begin .. wpr-1
+struct RimRows {
+  int a0, a1;  // rows [a0, a1) and [b0, b1) are recomputed completely
+  int b0, b1;
+  int p0, p1;  // of the rows [p0, p1): word 0 if `head`, and the words tail_begin .. wpr-1
+  int head, tail_begin;
+};
+
+__global__ void __launch_bounds__(128) half_sweep_rim_kernel(SweepParams P, RimRows R) {
   const Geom& g = P.g;
-  const int full_rows = rb + (g.rows - re);
-  const int per_row = head + (g.wpr - tail_begin);
-  const long long per_rep = (long long)full_rows * g.wpr + (long long)per_row * (re - rb);
+  const int na = R.a1 - R.a0, nb = R.b1 - R.b0;
+  const int full_rows = na + nb;
+  const int per_row = R.head + (g.wpr - R.tail_begin);
+  const long long per_rep = (long long)full_rows * g.wpr + (long long)per_row * (R.p1 - R.p0);
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= per_rep * g.n_replicas) return;
   const int rep = (int)(tid / per_rep);
@@ -286,12 +294,12 @@ __global__ void __launch_bounds__(128) half_sweep_rim_kernel(SweepParams P, int 
   if (rem < full_rows * g.wpr) {
     const int r = rem / g.wpr;
     w = rem - r * g.wpr;
-    i = r < rb ? r : re + (r - rb);
+    i = r < na ? R.a0 + r : R.b0 + (r - na);
   } else {
     const int e = rem - full_rows * g.wpr;
     const int r = e / per_row, k = e - r * per_row;
-    i = rb + r;
-    w = (head && k == 0) ? 0 : tail_begin + (k - head);
+    i = R.p0 + r;
+    w = (R.head && k == 0) ? 0 : R.tail_begin + (k - R.head);
   }
   generic_update_one(P, P.colour, P.sweep, rep, i, w);
 }
@@ -533,10 +541,8 @@ struct Tuning {
     jit_unroll = num("TSU_JIT_UNROLL", 0);
   }
 };
-const Tuning& tuning() {
-  static const Tuning t;
-  return t;
-}
+Tuning g_tuning;  // read when the library is loaded; tsu_ising2d_reload_tuning() reads the environment again
+const Tuning& tuning() { return g_tuning; }
 constexpr int kDefaultW = 4, kDefaultJitW = 4, kDefaultJitMinB = 4;
 
 Geom make_geom(int n_replicas, int rows, int cols, int wrap_rows, int wrap_cols, int row0) {
@@ -615,7 +621,9 @@ JitKernel jit_function(int handle) {
 int launch_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows, int wrap_cols, int colour,
                       const uint32_t* d_lut, const int32_t* d_lut_index, uint64_t seed, uint32_t sweep,
                       uint32_t replica0, int row0, const uint32_t* d_halo_top, const uint32_t* d_halo_bot,
-                      cudaStream_t st, JitKernel jit = JitKernel{nullptr, 0}) {
+                      cudaStream_t st, JitKernel jit = JitKernel{nullptr, 0}, int upd_begin = 0, int upd_end = -1) {
+  if (upd_end < 0) upd_end = rows;  // local rows [upd_begin, upd_end) are updated (default: all)
+  if (upd_begin >= upd_end) return TSU_OK;
   SweepParams P;
   P.state = d_state;
   P.lut = d_lut;
@@ -635,12 +643,13 @@ int launch_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int
   // rows that have a north / south neighbour (exactly the cases opp_row() resolves): the wide kernel takes those,
   // columns treated as periodic; what that gets wrong on open lattices is redone by the rim pass
   const bool north_ok = d_halo_top || wrap_rows, south_ok = d_halo_bot || wrap_rows;
-  const int rb = north_ok ? 0 : 1, re = south_ok ? rows : rows - 1;
+  const int rb0 = north_ok ? 0 : 1, re0 = south_ok ? rows : rows - 1;
+  const int rb = rb0 > upd_begin ? rb0 : upd_begin, re = re0 < upd_end ? re0 : upd_end;  // rows of the wide kernel
   // words that are full for both row parities: floor(cols / 2) lanes exist in every row of either colour
   const int full_words = (cols / 2) / 32;
   const bool ragged = cols % 256 != 0;
   const int nvec_f = ragged ? full_words / 4 : P.g.wpr / 4;
-  const bool need_rim = rb > 0 || re < rows || !wrap_cols || ragged;
+  const bool need_rim = rb > upd_begin || re < upd_end || !wrap_cols || ragged;
   bool fast = nvec_f >= 1 && re - rb >= 1;
   if (need_rim && tuning().open_generic) fast = false;
   if (fast) {
@@ -671,15 +680,22 @@ int launch_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int
       half_sweep_fast_kernel<4, 4><<<grid, 128, 0, st>>>(P);
     }
     if (need_rim) {
-      const int head = (ragged || !wrap_cols) ? 1 : 0;
-      const int tail_begin = ragged ? 4 * nvec_f : (wrap_cols ? P.g.wpr : P.g.wpr - 1);
-      const long long per_rep = (long long)(rb + rows - re) * P.g.wpr + (long long)(head + P.g.wpr - tail_begin) * frows;
-      half_sweep_rim_kernel<<<blocks_for(per_rep * n_replicas, 128), 128, 0, st>>>(P, rb, re, head, tail_begin);
+      RimRows R;
+      R.a0 = upd_begin; R.a1 = rb;   // updated rows above / below the wide kernel's range (no north / south neighbour)
+      R.b0 = re; R.b1 = upd_end;
+      R.p0 = rb; R.p1 = re;
+      R.head = (ragged || !wrap_cols) ? 1 : 0;
+      R.tail_begin = ragged ? 4 * nvec_f : (wrap_cols ? P.g.wpr : P.g.wpr - 1);
+      const long long per_rep = (long long)((R.a1 - R.a0) + (R.b1 - R.b0)) * P.g.wpr +
+                                (long long)(R.head + P.g.wpr - R.tail_begin) * frows;
+      if (per_rep > 0) half_sweep_rim_kernel<<<blocks_for(per_rep * n_replicas, 128), 128, 0, st>>>(P, R);
     }
   } else {
     P.strip_rows = 1;
     P.n_strips = rows;
-    const long long total = (long long)n_replicas * rows * P.g.wpr;
+    P.row_begin = upd_begin;
+    P.row_end = upd_end;
+    const long long total = (long long)n_replicas * (upd_end - upd_begin) * P.g.wpr;
     half_sweep_generic_kernel<<<blocks_for(total, 128), 128, 0, st>>>(P);
   }
   cudaError_t e = cudaGetLastError();
@@ -716,6 +732,8 @@ int launch_resident_sweeps(uint32_t* d_state, int n_replicas, int rows, int cols
 }  // namespace
 
 extern "C" {
+
+void tsu_ising2d_reload_tuning(void) { g_tuning = Tuning(); }
 
 int64_t tsu_ising2d_words_per_row(int cols) { return cols > 0 ? words_per_row(cols) : 0; }
 
@@ -760,6 +778,20 @@ int tsu_ising2d_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols
   TSU_CHECK_ARG(!wrap_rows || (rows % 2 == 0 && rows > 2) || d_halo_top || d_halo_bot);
   return launch_half_sweep(d_state, n_replicas, rows, cols, wrap_rows, wrap_cols, colour, d_lut, d_lut_index, seed,
                            sweep, replica0, row0, d_halo_top, d_halo_bot, tsu_stream(stream));
+}
+
+int tsu_ising2d_half_sweep_rows(int jit_handle, uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows,
+                                int wrap_cols, int colour, const uint32_t* d_lut, const int32_t* d_lut_index, uint64_t seed,
+                                uint32_t sweep, uint32_t replica0, int row0, const uint32_t* d_halo_top,
+                                const uint32_t* d_halo_bot, int row_begin, int row_end, uintptr_t stream) {
+  TSU_CHECK_ARG(d_state && d_lut && geom_ok(n_replicas, rows, cols) && rows_ok(rows, row0));
+  TSU_CHECK_ARG(colour == 0 || colour == 1);
+  TSU_CHECK_ARG(!wrap_cols || (cols % 2 == 0 && cols > 2));
+  TSU_CHECK_ARG(!wrap_rows || (rows % 2 == 0 && rows > 2) || d_halo_top || d_halo_bot);
+  TSU_CHECK_ARG(row_begin >= 0 && row_begin <= row_end && row_end <= rows);
+  const JitKernel jit = (jit_handle > 0 && !d_lut_index) ? jit_function(jit_handle) : JitKernel{nullptr, 0};
+  return launch_half_sweep(d_state, n_replicas, rows, cols, wrap_rows, wrap_cols, colour, d_lut, d_lut_index, seed, sweep,
+                           replica0, row0, d_halo_top, d_halo_bot, tsu_stream(stream), jit, row_begin, row_end);
 }
 
 int tsu_ising2d_sweeps(uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows, int wrap_cols,

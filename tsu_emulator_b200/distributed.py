@@ -4,8 +4,9 @@ Multi-GPU drivers (one process per GPU, torch.distributed; NCCL over NVLink on t
   * SlabShardedIsing2D - ONE large lattice (or a batch of them) split into contiguous row slabs.  Per
     half-sweep every rank needs the opposite-colour row just above and just below its slab: the rows that
     were updated in the previous half-sweep are sent to the ring neighbours (wpr words per replica and
-    side: 8 KiB for 131072 columns).  Philox counters use global row indices, so the bits are identical to
-    the single-GPU run for any number of ranks.
+    side: 8 KiB for 131072 columns).  The two boundary rows are updated first on a side stream and sent while
+    the interior rows are updated on the main stream.  Philox counters use global row indices, so the bits
+    are identical to the single-GPU run for any number of ranks.
   * replica_shard - independent replicas / chains / ladders: contiguous index ranges, no collective.
   * LatticeTempering - K temperature ladders x R temperatures of one lattice size with replica exchange
     (tsu/gibbs.py:238-338 semantics on the lattice kernels).  Lattices never move: the swap permutes the
@@ -40,12 +41,20 @@ class SlabShardedIsing2D:
 
     engine_factory(local_rows, row0) must return an engine exposing
         .state                      tensor [n_replicas, 2, local_rows, wpr] (int32 words)
-        .half_sweep(colour, halo_top=..., halo_bot=...)   halos: [n_replicas, wpr] or None
+        .half_sweep(colour, halo_top=..., halo_bot=..., rows=(begin, end))   halos: [n_replicas, wpr] or None
         .sweep_index                incremented by the driver
         .observables_tensor(next_rows=...) -> int64 [n_replicas, 2]
+
+    Overlap (default on CUDA engines with at least 4 local rows): a half-sweep of colour c is issued as
+      side stream : rows 0 and L-1 (they need the halos of colour 1-c), then the exchange of the new rows 0 / L-1
+      main stream : rows 1 .. L-2 (no halo needed)
+    so the 2 x wpr-word messages (8 KiB per side at 131072 columns) and the two one-row launches hide behind the
+    interior update.  Dependencies between consecutive half-sweeps are two events: the interior waits for the
+    previous boundary update (it reads and overwrites the rows next to it), the boundary update waits for the
+    previous interior update.  Same launches, same Philox coordinates, same bits as the serial order.
     """
 
-    def __init__(self, rows: int, cols: int, engine_factory, periodic: bool = True, group=None):
+    def __init__(self, rows: int, cols: int, engine_factory, periodic: bool = True, group=None, overlap=None):
         dist = _dist()
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -60,50 +69,59 @@ class SlabShardedIsing2D:
 
         st = self.engine.state
         self.n_replicas, self.wpr = st.shape[0], st.shape[3]
-        self.halo_top = torch.zeros((self.n_replicas, self.wpr), dtype=st.dtype, device=st.device)
-        self.halo_bot = torch.zeros_like(self.halo_top)
+        # halo[colour][0 = above row0, 1 = below the last local row]
+        self.halo = torch.zeros((2, 2, self.n_replicas, self.wpr), dtype=st.dtype, device=st.device)
         self._next_rows = torch.zeros((self.n_replicas, 2, self.wpr), dtype=st.dtype, device=st.device)
         self.up = (self.rank - 1) % self.world     # owns the rows above mine
         self.down = (self.rank + 1) % self.world   # owns the rows below mine
         self.has_up = self.periodic or self.rank > 0
         self.has_down = self.periodic or self.rank < self.world - 1
+        self.overlap = (self.local_rows >= 4) if overlap is None else bool(overlap)
+        self._side = None
+        if self.overlap and st.is_cuda:
+            self._side = torch.cuda.Stream(device=st.device, priority=-1)
+
+    @property
+    def halo_top(self):  # halos of the colour exchanged last (kept for callers of exchange())
+        return self.halo[self._last_colour, 0]
+
+    @property
+    def halo_bot(self):
+        return self.halo[self._last_colour, 1]
+
+    _last_colour = 0
 
     # -- halo exchange ---------------------------------------------------------------------------
     def exchange(self, colour: int):
-        """make rows (row0-1) and (row0+local_rows) of `colour` available as halo_top / halo_bot"""
+        """make rows (row0-1) and (row0+local_rows) of `colour` available as halo[colour][0] / halo[colour][1]"""
         st = self.engine.state
+        self._last_colour = colour
+        top, bot = self.halo[colour, 0], self.halo[colour, 1]
         if self.world == 1:
             if self.periodic:
-                self.halo_top.copy_(st[:, colour, -1, :])
-                self.halo_bot.copy_(st[:, colour, 0, :])
+                top.copy_(st[:, colour, -1, :])
+                bot.copy_(st[:, colour, 0, :])
             return
         dist = _dist()
         first = st[:, colour, 0, :].contiguous()
         last = st[:, colour, -1, :].contiguous()
-        if self.world == 2 and self.periodic:
-            # both neighbours are the same peer: order the two messages explicitly
-            peer = self._peer(self.up)
-            if self.rank == 0:
-                dist.send(first, peer, self.group)
-                dist.recv(self.halo_bot, peer, self.group)
-                dist.send(last, peer, self.group)
-                dist.recv(self.halo_top, peer, self.group)
-            else:
-                dist.recv(self.halo_bot, peer, self.group)
-                dist.send(first, peer, self.group)
-                dist.recv(self.halo_top, peer, self.group)
-                dist.send(last, peer, self.group)
-            return
         ops = []
-        if self.has_up:
-            ops.append(dist.P2POp(dist.isend, first, self._peer(self.up), self.group))
-            ops.append(dist.P2POp(dist.irecv, self.halo_top, self._peer(self.up), self.group))
-        if self.has_down:
-            ops.append(dist.P2POp(dist.isend, last, self._peer(self.down), self.group))
-            ops.append(dist.P2POp(dist.irecv, self.halo_bot, self._peer(self.down), self.group))
+        if self.world == 2 and self.periodic:
+            # both neighbours are the same peer: messages to one peer match in posting order, so both ranks post
+            # (first, last) and receive (the peer's first row = below me, the peer's last row = above me)
+            peer = self._peer(self.up)
+            ops = [dist.P2POp(dist.isend, first, peer, self.group), dist.P2POp(dist.isend, last, peer, self.group),
+                   dist.P2POp(dist.irecv, bot, peer, self.group), dist.P2POp(dist.irecv, top, peer, self.group)]
+        else:
+            if self.has_up:
+                ops.append(dist.P2POp(dist.isend, first, self._peer(self.up), self.group))
+                ops.append(dist.P2POp(dist.irecv, top, self._peer(self.up), self.group))
+            if self.has_down:
+                ops.append(dist.P2POp(dist.isend, last, self._peer(self.down), self.group))
+                ops.append(dist.P2POp(dist.irecv, bot, self._peer(self.down), self.group))
         if ops:
             for req in dist.batch_isend_irecv(ops):
-                req.wait()
+                req.wait()  # CUDA: the current stream waits for the transfer; gloo: the host does
 
     def _peer(self, group_rank: int) -> int:
         dist = _dist()
@@ -111,29 +129,72 @@ class SlabShardedIsing2D:
             return group_rank
         return dist.get_global_rank(self.group, group_rank)
 
+    def _halos(self, colour: int):
+        """halo rows a half-sweep of `colour` reads (the other colour)"""
+        opp = 1 - colour
+        return (self.halo[opp, 0] if self.has_up else None), (self.halo[opp, 1] if self.has_down else None)
+
     # -- updates -----------------------------------------------------------------------------------
     def half_sweep(self, colour: int):
+        """serial form: exchange, then one launch for all local rows"""
         self.exchange(1 - colour)
-        self.engine.half_sweep(colour, halo_top=self.halo_top if self.has_up else None,
-                               halo_bot=self.halo_bot if self.has_down else None)
+        top, bot = self._halos(colour)
+        self.engine.half_sweep(colour, halo_top=top, halo_bot=bot)
 
     def sweep(self, n_sweeps: int = 1):
+        if not self.overlap:
+            for _ in range(n_sweeps):
+                self.half_sweep(0)
+                self.half_sweep(1)
+                self.engine.sweep_index += 1
+            return self
+        import contextlib
+
+        import torch
+
+        cuda = self._side is not None
+        main = torch.cuda.current_stream(self.engine.state.device) if cuda else None
+        on_side = (lambda: torch.cuda.stream(self._side)) if cuda else contextlib.nullcontext
+        L = self.local_rows
+        ev_interior = ev_boundary = None
+        with on_side():
+            if cuda:
+                self._side.wait_stream(main)
+            self.exchange(1)  # colour 0 goes first and reads colour 1
         for _ in range(n_sweeps):
-            self.half_sweep(0)
-            self.half_sweep(1)
+            for colour in (0, 1):
+                top, bot = self._halos(colour)
+                # interior on the main stream
+                if cuda and ev_boundary is not None:
+                    main.wait_event(ev_boundary)
+                self.engine.half_sweep(colour, rows=(1, L - 1))
+                ev_prev_interior = ev_interior
+                if cuda:
+                    ev_interior = torch.cuda.Event()
+                    ev_interior.record(main)
+                # boundary rows and the exchange of what they produce on the side stream
+                with on_side():
+                    if cuda and ev_prev_interior is not None:
+                        self._side.wait_event(ev_prev_interior)
+                    self.engine.half_sweep(colour, halo_top=top, halo_bot=bot, rows=(0, 1))
+                    self.engine.half_sweep(colour, halo_top=top, halo_bot=bot, rows=(L - 1, L))
+                    if cuda:
+                        ev_boundary = torch.cuda.Event()
+                        ev_boundary.record(self._side)
+                    self.exchange(colour)
             self.engine.sweep_index += 1
+        if cuda:
+            main.wait_stream(self._side)
         return self
 
     # -- observables -------------------------------------------------------------------------------
     def observables(self):
         """global (# up spins, # anti-aligned bonds) per replica, summed over the slabs"""
-        import torch
-
         nxt = None
         if self.periodic or self.world > 1:
             for colour in (0, 1):          # collective: every rank takes part even if it has no lower neighbour
                 self.exchange(colour)
-                self._next_rows[:, colour, :] = self.halo_bot
+                self._next_rows[:, colour, :] = self.halo[colour, 1]
             if self.has_down:
                 nxt = self._next_rows
         obs = self.engine.observables_tensor(next_rows=nxt).clone()

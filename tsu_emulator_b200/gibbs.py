@@ -56,8 +56,11 @@ class _DenseProblem:
         torch = _lib.require_cuda()
         J = _as_square(coupling)
         self.N = J.shape[0]
+        if precision == "bf16":
+            raise ValueError("precision='bf16' (tensor cores) serves sample_boltzmann / sample / sample_chains; "
+                             "this entry point needs a 'float64' or 'float32' sampler")
         if precision not in ("float64", "float32"):
-            raise ValueError("precision must be 'float64' or 'float32'")
+            raise ValueError("precision must be 'float64', 'float32' or 'bf16'")
         self.np_dtype = np.float64 if precision == "float64" else np.float32
         self.code = 1 if precision == "float64" else 0
         self.device = device
@@ -69,6 +72,46 @@ class _DenseProblem:
             self.bias = torch.from_numpy(np.ascontiguousarray(b.astype(self.np_dtype))).to(device)
         else:
             self.bias = None
+
+
+TC_MAX_N = 4096   # csrc/dense_tc.cu keeps the chain bits of a CTA in shared memory
+TC_PANEL = 128
+
+
+class _TcProblem:
+    """couplings of the tensor-core path (csrc/dense_tc.cu): bf16, row-major, N padded with uncoupled sites to a
+    multiple of the 128-site panel (their bits are dropped again; a site's uniform depends only on
+    (seed, chain, sweep, site), so the padding does not change what the real sites draw)."""
+
+    def __init__(self, coupling, bias, device, update_order):
+        torch = _lib.require_cuda()
+        J = _as_square(coupling)
+        self.N = J.shape[0]
+        self.Np = (self.N + TC_PANEL - 1) // TC_PANEL * TC_PANEL
+        if self.Np > TC_MAX_N:
+            raise ValueError(f"precision='bf16' (tensor-core path) supports at most {TC_MAX_N} bits; got {self.N}")
+        if update_order != "sequential":
+            raise ValueError("precision='bf16' (tensor-core path) implements the sequential update order only")
+        self.device = device
+        Jp = np.zeros((self.Np, self.Np), dtype=np.float32)
+        Jp[:self.N, :self.N] = J
+        self.J = torch.from_numpy(Jp).to(device=device, dtype=torch.bfloat16).contiguous()
+        self.bias = None
+        if bias is not None:
+            b = np.asarray(bias, dtype=np.float64)
+            if b.shape != (self.N,):
+                raise ValueError("bias must have one entry per bit")
+            bp = np.zeros(self.Np, dtype=np.float32)
+            bp[:self.N] = b
+            self.bias = torch.from_numpy(bp).to(device)
+
+    def pad_state(self, st):
+        if self.Np == self.N:
+            return st
+        torch = _lib.require_cuda()
+        out = torch.zeros((st.shape[0], self.Np), dtype=torch.uint8, device=st.device)
+        out[:, :self.N] = st
+        return out
 
 
 class GibbsSampler:
@@ -83,10 +126,13 @@ class GibbsSampler:
                  precision: str = "float64", device=None):
         self.config = config or GibbsConfig()
         self.sample_count = 0
+        if precision not in ("float64", "float32", "bf16"):
+            raise ValueError("precision must be 'float64', 'float32' or 'bf16'")
         self.precision = precision
         self._seed = int(seed) if seed is not None else int(np.random.randint(0, 2**31 - 1))
         self._sweep_counter = 0  # Philox offset: advances with every sweep executed
         self._chain_counter = 0
+        self._swap_counter = 0   # Philox offset of the replica-exchange draws: advances with every swap pass
         self._device = device
 
     # ------------------------------------------------------------------ scalar helpers
@@ -153,12 +199,16 @@ class GibbsSampler:
         self._sweep_counter += total
         return samples, energy, best_state, best_energy
 
-    def _initial_states(self, prob: _DenseProblem, n_chains: int, initial_state=None):
+    def _initial_states(self, prob, n_chains: int, initial_state=None):
         torch = _lib.require_cuda()
         if initial_state is not None:
             a = np.asarray(initial_state)
             if a.ndim == 1:
+                if a.shape != (prob.N,):
+                    raise ValueError(f"initial_state must have {prob.N} entries, got shape {a.shape}")
                 a = np.broadcast_to(a, (n_chains, prob.N))
+            elif a.shape != (n_chains, prob.N):
+                raise ValueError(f"initial_state must have shape ({prob.N},) or ({n_chains}, {prob.N}), got {a.shape}")
             return torch.from_numpy(np.ascontiguousarray((a != 0).astype(np.uint8))).to(prob.device)
         state = torch.empty((n_chains, prob.N), dtype=torch.uint8, device=prob.device)
         with torch.cuda.device(prob.device):
@@ -208,8 +258,13 @@ class GibbsSampler:
         n_chains == 1 (default): int array (n_samples, n_bits) like the reference.
         n_chains > 1: (n_chains, n_samples, n_bits) - independent chains run concurrently.
         """
-        prob = _DenseProblem(coupling, bias, self.precision, self._dev())
         burnin = burnin if burnin is not None else self.config.n_burnin
+        if self.precision == "bf16":
+            if _uniforms is not None or _orders is not None:
+                raise ValueError("injected draws are a float64 / float32 parity mode; precision='bf16' draws Philox")
+            return self._sample_boltzmann_tensor(coupling, bias, int(n_samples), int(burnin), initial_state,
+                                                 int(n_chains), as_tensor)
+        prob = _DenseProblem(coupling, bias, self.precision, self._dev())
         st = self._initial_states(prob, int(n_chains), initial_state)
         u, o = self._inject(prob, _uniforms, _orders)
         samples, _, _, _ = self._run(prob, st, n_burnin=int(burnin), n_samples=int(n_samples),
@@ -227,41 +282,57 @@ class GibbsSampler:
         """README.md:69-80: `sampler.sample(J, n_samples=1000)` -> (n_samples, n_bits) binary configurations"""
         return self.sample_boltzmann(J, n_samples=n_samples, **kwargs)
 
+    def _tc_sweeps(self, prob: "_TcProblem", st, n_sweeps: int, fields=None):
+        """n_sweeps sequential sweeps of all chains of `st` ([n_chains, Np] uint8, in place) on the tensor cores"""
+        torch = _lib.require_cuda()
+        if n_sweeps <= 0:
+            return
+        with torch.cuda.device(prob.device):
+            _lib.call("tsu_dense_gibbs_tc_run", ptr(prob.J), ptr(prob.bias), ptr(st), int(st.shape[0]), prob.Np,
+                      float(self.config.temperature), None, int(n_sweeps), self._seed,
+                      self._sweep_counter & 0xFFFFFFFF, self._chain_counter & 0xFFFFFFFF, ptr(fields),
+                      _lib.current_stream())
+        self._sweep_counter += int(n_sweeps)
+
+    def _sample_boltzmann_tensor(self, coupling, bias, n_samples, burnin, initial_state, n_chains, as_tensor):
+        """tsu/gibbs.py:198-211 on csrc/dense_tc.cu: burn-in sweeps, then n_samples x config.n_sweeps sweeps with the
+        state of every chain recorded after each group; bf16 couplings, fp32 fields accumulated in TMEM"""
+        torch = _lib.require_cuda()
+        prob = _TcProblem(coupling, bias, self._dev(), self.config.update_order)
+        st = prob.pad_state(self._initial_states(prob, n_chains, initial_state))
+        samples = torch.empty((n_samples, n_chains, prob.N), dtype=torch.uint8, device=prob.device)
+        self._tc_sweeps(prob, st, burnin)
+        for k in range(n_samples):
+            self._tc_sweeps(prob, st, self.config.n_sweeps)
+            samples[k] = st[:, :prob.N]
+        self._chain_counter += n_chains
+        self.sample_count += n_samples
+        if as_tensor:
+            return samples if n_chains > 1 else samples[:, 0]
+        out = samples.cpu().numpy().astype(int)
+        if n_chains == 1:
+            return out[:, 0, :]
+        return np.ascontiguousarray(out.transpose(1, 0, 2))
+
     def _sample_chains_tensor(self, coupling, bias, n_chains, n_sweeps, initial_state, as_tensor, return_energy):
         """tensor-core path (csrc/dense_tc.cu): bf16 couplings, fp32 fields accumulated in TMEM"""
         torch = _lib.require_cuda()
-        device = self._dev()
-        J = _as_square(coupling)
-        N = J.shape[0]
-        if N % 128 or N > 4096:
-            raise ValueError("the tensor-core path needs N % 128 == 0 and N <= 4096")
-        if self.config.update_order != "sequential":
-            raise ValueError("the tensor-core path implements the sequential update order")
-        Jd = torch.from_numpy(np.ascontiguousarray(J)).to(device=device, dtype=torch.bfloat16).contiguous()
-        bd = None
-        if bias is not None:
-            bd = torch.from_numpy(np.ascontiguousarray(np.asarray(bias, dtype=np.float32))).to(device)
-
-        class _P:  # minimal problem record for _initial_states
-            pass
-        prob = _P()
-        prob.N, prob.device = N, device
-        st = self._initial_states(prob, int(n_chains), initial_state)
-        with torch.cuda.device(device):
-            _lib.call("tsu_dense_gibbs_tc_run", ptr(Jd), ptr(bd), ptr(st), int(n_chains), N,
-                      float(self.config.temperature), None, int(n_sweeps), self._seed,
-                      self._sweep_counter & 0xFFFFFFFF, self._chain_counter & 0xFFFFFFFF, None, _lib.current_stream())
-        self._sweep_counter += int(n_sweeps)
+        prob = _TcProblem(coupling, bias, self._dev(), self.config.update_order)
+        device, N = prob.device, prob.N
+        st = prob.pad_state(self._initial_states(prob, int(n_chains), initial_state))
+        self._tc_sweeps(prob, st, int(n_sweeps))
         self._chain_counter += int(n_chains)
         energy = None
         if return_energy:  # E = -1/2 s^T J s - b^T s from one more tensor-core field evaluation
-            H = torch.empty((n_chains, N), dtype=torch.float32, device=device)
+            H = torch.empty((n_chains, prob.Np), dtype=torch.float32, device=device)
             with torch.cuda.device(device):
-                _lib.call("tsu_dense_tc_debug_fields", ptr(Jd), ptr(st), int(n_chains), N, ptr(H), _lib.current_stream())
+                _lib.call("tsu_dense_tc_debug_fields", ptr(prob.J), ptr(st), int(n_chains), prob.Np, ptr(H),
+                          _lib.current_stream())
             sf = st.to(torch.float64)
             energy = -0.5 * (sf * H.to(torch.float64)).sum(1)
-            if bd is not None:
-                energy = energy - sf @ bd.to(torch.float64)
+            if prob.bias is not None:
+                energy = energy - sf @ prob.bias.to(torch.float64)
+        st = st[:, :N]
         out = st if as_tensor else st.cpu().numpy().astype(int)
         if return_energy:
             return out, (energy if as_tensor else energy.cpu().numpy())
@@ -332,9 +403,10 @@ class GibbsSampler:
                 wu = None
                 if inj is not None:
                     wu = torch.from_numpy(np.ascontiguousarray(np.asarray(inj["swap_uniforms"][it], dtype=np.float64))).to(device)
+                self._swap_counter += 1
                 with torch.cuda.device(device):
                     _lib.call("tsu_pt_swap", ptr(e), ptr(T_slot), ptr(slot_replica), None, 1, R, self._seed,
-                              (it + 1) & 0xFFFFFFFF, ptr(stats), ptr(wu), 0, _lib.current_stream())
+                              self._swap_counter & 0xFFFFFFFF, ptr(stats), ptr(wu), 0, _lib.current_stream())
                 T_chain[slot_replica.long()] = T_slot
             samples[it] = states[slot_replica[0].long()]
         self._chain_counter += R
@@ -384,15 +456,29 @@ class GibbsSampler:
         return state, self.compute_energy(state, J, None if bias is None else np.asarray(bias, dtype=np.float64))
 
 
+def _bf16_exact(coupling) -> bool:
+    """every coupling survives rounding to bf16 (8 significant bits) and the matrix fits the tensor-core kernel"""
+    J = np.asarray(coupling, dtype=np.float64)
+    if J.ndim != 2 or J.shape[0] != J.shape[1] or J.shape[0] > TC_MAX_N:
+        return False
+    u = J.astype(np.float32).view(np.uint32)
+    rounded = ((u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).view(np.float32)
+    return bool(np.array_equal(rounded.astype(np.float64), J))
+
+
 class HardwareEmulator:
     """tsu/gibbs.py:396-487.  The timing model is the reference's arithmetic; sample_parallel finally runs
     its `parallel_chains` chains in parallel (the reference loops over them, gibbs.py:475-479)."""
 
-    def __init__(self, n_bits: int = 100, clock_speed_ghz: float = 1.0, parallel_chains: int = 1000):
+    def __init__(self, n_bits: int = 100, clock_speed_ghz: float = 1.0, parallel_chains: int = 1000, *,
+                 precision: str = "auto"):
         self.n_bits = n_bits
         self.clock_speed_ghz = clock_speed_ghz
         self.parallel_chains = parallel_chains
         self.ns_per_cycle = 1.0 / clock_speed_ghz
+        # "auto": the tensor-core path when the couplings are exactly representable in bf16 (e.g. +-1 / integer
+        # graphs) and there are enough chains to fill a 64-chain tile; otherwise float64 fields
+        self.precision = precision
 
     def estimate_hardware_time(self, n_samples: int, n_sweeps_per_sample: int) -> dict:
         """tsu/gibbs.py:421-448"""
@@ -415,9 +501,12 @@ class HardwareEmulator:
         """tsu/gibbs.py:450-487: min(parallel_chains, n_samples) chains x ceil(n_samples/parallel_chains)
         samples each (burn-in 100), stacked chain after chain and truncated to n_samples."""
         config = GibbsConfig(temperature=temperature)
-        sampler = GibbsSampler(config)
         samples_per_chain = int(np.ceil(n_samples / self.parallel_chains))
         n_chains = min(self.parallel_chains, n_samples)
+        precision = self.precision
+        if precision == "auto":
+            precision = "bf16" if (n_chains >= 64 and _bf16_exact(coupling)) else "float64"
+        sampler = GibbsSampler(config, precision=precision)
         out = sampler.sample_boltzmann(coupling, n_samples=samples_per_chain, burnin=100, n_chains=n_chains)
         if n_chains == 1:
             out = out[None]

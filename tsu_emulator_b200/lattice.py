@@ -260,10 +260,21 @@ class Ising2DEngine:
         return self.spins_tensor(pm1).cpu().numpy().astype(np.int64)
 
     # ------------------------------------------------------------------ updates
-    def half_sweep(self, colour: int, halo_top=None, halo_bot=None, uniforms=None):
-        """resample every site of `colour`; halos are [n_replicas, wpr] int32 rows of the other colour."""
+    def half_sweep(self, colour: int, halo_top=None, halo_bot=None, uniforms=None, rows=None):
+        """resample every site of `colour`; halos are [n_replicas, wpr] int32 rows of the other colour.
+        rows=(begin, end) restricts the update to those local rows (same bits for any split of the rows)."""
         with self._torch.cuda.device(self.device):
-            if uniforms is None and self.lut_index is None and getattr(self, "_jit", 0) > 0:
+            if rows is not None:
+                if uniforms is not None:
+                    raise ValueError("row ranges are not available in injected-uniform mode")
+                _lib.call(
+                    "tsu_ising2d_half_sweep_rows", int(getattr(self, "_jit", 0)) if self.lut_index is None else 0,
+                    ptr(self.state), self.n_replicas, self.rows, self.cols,
+                    int(self.wrap_rows and not self.is_slab), int(self.wrap_cols), int(colour), ptr(self.lut),
+                    ptr(self.lut_index), self.seed, self.sweep_index & 0xFFFFFFFF, self.replica0, self.row0,
+                    ptr(halo_top), ptr(halo_bot), int(rows[0]), int(rows[1]), _lib.current_stream(),
+                )
+            elif uniforms is None and self.lut_index is None and getattr(self, "_jit", 0) > 0:
                 _lib.call(
                     "tsu_ising2d_half_sweep_jit", self._jit, ptr(self.state), self.n_replicas, self.rows, self.cols,
                     int(self.wrap_rows and not self.is_slab), int(self.wrap_cols), int(colour), ptr(self.lut),

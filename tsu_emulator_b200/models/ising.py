@@ -230,7 +230,11 @@ class IsingGrid(IsingModel):
         return h0 if np.all(self.h == h0) else None
 
     def _lattice_ok(self) -> bool:
-        """the stencil kernel covers uniform J (untouched wiring) and a uniform field"""
+        """the stencil kernel covers uniform J (untouched wiring), a uniform field and bipartite lattices: a periodic
+        dimension of odd length closes odd cycles, the two-colour update does not apply and the grid takes the
+        dense-J path like any other IsingModel (the reference wires any size, ising.py:343-361)"""
+        if self.periodic and (self.rows % 2 or self.cols % 2):
+            return False
         return self._J is None and self._uniform_field() is not None
 
     def sample(self, n_samples: int = 1000, initial_state: Optional[np.ndarray] = None, *, n_replicas: int = 1,
