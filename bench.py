@@ -13,11 +13,20 @@ collective): weak scaling.
 value  : updates/s with the lattices resident in HBM (CUDA events, max over ranks).
 e2e    : the same through the host API with HOST buffers: every step uploads the packed initial
          lattices from pinned host memory (chunked, overlapped with the sweeps of the previous
-         chunk), runs the sweeps and reads magnetisation/energy back.
+         chunk), runs the sweeps and reads magnetisation/energy back.  `h2d_only` is the upload
+         alone (same chunks, all ranks at once): the host-side ceiling of the end-to-end number.
 roofline: HBM bound; algorithmic bytes = 0.25 B per spin update (read 1 neighbour-colour bit,
-         write 1 bit), per half-sweep launch, against the measured copy bandwidth.
-cpu_baseline: the oracle's literal port of the reference's per-spin NumPy loop
-         (oracle/ising2d_oracle.py:gibbs_sweep_port, tsu/gibbs.py:128-162) on the host cores.
+         write 1 bit), per half-sweep launch, against the measured copy bandwidth.  `math_issue`
+         is the limiter this kernel actually runs into.
+cpu_baseline / --impl reference: the UNMODIFIED reference (GibbsSampler.gibbs_sweep of tsu/gibbs.py,
+         from oracle/_ref or /root/reference) on the host cores, one process per core, on a bounded
+         sample of the workload; the oracle's literal port only if the reference tree is not there.
+secondary: the other BASELINE configurations, timed with CUDA events inside this run:
+         C1 (IsingModel2D 50 x 50, 1000 gibbs_update + M + E), C3 (dense SK N = 4096, 2048 chains,
+         10 sweeps on tcgen05; tensor roofline), C5 (50-temperature ladders of 1024^2 lattices with
+         replica exchange; Langevin 1e6 chains x dim 10, float64 and float32) and C4 (131072^2 as row
+         slabs).  Under --gpus N > 1 the row slabs (strong and weak) and the ladders are sharded over
+         the N ranks, so the scaling run times the halo exchange and the energy all-gather.
 """
 
 import argparse
@@ -39,46 +48,74 @@ BYTES_PER_UPDATE = 0.25
 WORKLOAD = "ising2d_8192x8192_T2.269_periodic_4096replicas_checkerboard_gibbs"
 METRIC = "spin_updates_per_s"
 UNIT = "spin-updates/s"
+CPU_SIZE, CPU_SWEEPS = 64, 30   # bounded sample of the workload for the host-core arm
 
 
-# ----------------------------------------------------------------------------- CPU baseline
+# ----------------------------------------------------------------------------- CPU arm
 def _cpu_worker(args):
-    """one process: literal port of the reference loop on its own small periodic lattice"""
-    rank, size, n_sweeps = args
+    """one process = one host core: the reference's own sweep (or its literal port) on a small periodic lattice"""
+    rank, size, n_sweeps, use_ref = args
     import numpy as np
 
+    n = size * size
+    if use_ref:
+        from oracle import ref_loader
+
+        gibbs, _, ising = ref_loader.load_reference()
+        grid = ising.IsingGrid((size, size), J=1.0, config=ising.IsingConfig(temperature=TEMPERATURE), periodic=True)
+        Jb = 4.0 * grid.J
+        hb = 2.0 * grid.h - 2.0 * grid.J.sum(axis=1)      # spin -> bit transformation of the lattice couplings
+        sampler = gibbs.GibbsSampler(gibbs.GibbsConfig(temperature=TEMPERATURE))
+        np.random.seed(1000 + rank)
+        state = np.random.randint(0, 2, size=n)
+        t0 = time.perf_counter()
+        state = sampler.gibbs_sweep(state, Jb, hb, n_sweeps=n_sweeps)   # tsu/gibbs.py:128-162, unmodified
+        return time.perf_counter() - t0, int(state.sum())
     from oracle import ising2d_oracle as O
 
     rng = np.random.default_rng(1000 + rank)
     Jb, hb = O.dense_bit_model(size, size, 1.0, 0.0, True)
     order = O.checkerboard_order(size, size)
-    state = rng.integers(0, 2, size * size)
+    state = rng.integers(0, 2, n)
     t0 = time.perf_counter()
     for _ in range(n_sweeps):
-        state = O.gibbs_sweep_port(state, Jb, hb, TEMPERATURE, order, rng.random(size * size))
+        state = O.gibbs_sweep_port(state, Jb, hb, TEMPERATURE, order, rng.random(n))
     return time.perf_counter() - t0, int(state.sum())
 
 
-def cpu_baseline(size=64, n_sweeps=300, cores=None):
+def reference_tree_available():
+    try:
+        from oracle import make_ref
+
+        return make_ref.ref_root() is not None
+    except Exception:
+        return False
+
+
+def cpu_baseline(size=CPU_SIZE, n_sweeps=300, cores=None):
     """aggregate updates/s of `cores` independent replicas of a size x size lattice (bounded sample)"""
     import multiprocessing as mp
 
-    cores = cores or os.cpu_count() or 1
+    if not cores:
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    use_ref = reference_tree_available()
     ctx = mp.get_context("fork")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(r, size, n_sweeps) for r in range(cores)])
+        res = pool.map(_cpu_worker, [(r, size, n_sweeps, use_ref) for r in range(cores)])
     wall = time.perf_counter() - t0
     inner = max(r[0] for r in res)
     updates = cores * size * size * n_sweeps
+    what = ("the reference's own GibbsSampler.gibbs_sweep (tsu/gibbs.py:128-162, unmodified, oracle/_ref), "
+            "IsingGrid dense couplings" if use_ref else
+            "literal per-spin NumPy port of tsu/gibbs.py:128-162 (reference tree not available)")
     return {
         "value": updates / inner,
         "unit": UNIT,
         "cores": cores,
-        "kind": "port",
-        "sample": f"{cores} independent {size}x{size} periodic lattices x {n_sweeps} sweeps at T={TEMPERATURE}, "
-                  f"literal per-spin NumPy loop of tsu/gibbs.py:128-162 (dense {size*size}x{size*size} J), "
-                  f"one process per core; same update rule as the workload at reduced size",
+        "kind": "reference" if use_ref else "port",
+        "sample": f"{cores} independent {size}x{size} periodic lattices x {n_sweeps} sweeps at T={TEMPERATURE}: {what} "
+                  f"(dense {size*size}x{size*size} J), one process per core; same update rule as the workload at reduced size",
         "seconds": wall,
     }
 
@@ -91,11 +128,11 @@ def run_reference_arm(args):
     vals = []
     last = None
     for i in range(warmup + steps):
-        last = cpu_baseline(size=64, n_sweeps=30)
+        last = cpu_baseline(size=CPU_SIZE, n_sweeps=CPU_SWEEPS)
         if i >= warmup:
             vals.append(last["value"])
     v = sum(vals) / len(vals)
-    upd_per_step = last["cores"] * 64 * 64 * 30
+    upd_per_step = last["cores"] * CPU_SIZE * CPU_SIZE * CPU_SWEEPS
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -110,8 +147,9 @@ def run_reference_arm(args):
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference CPU path timed on a bounded sample of the workload"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+        "config": {"workload": WORKLOAD, "note": "reference CPU path timed on a bounded sample of the workload "
+                   f"({last['cores']} lattices of {CPU_SIZE}x{CPU_SIZE} x {CPU_SWEEPS} sweeps per step)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -124,16 +162,17 @@ class ClockSampler:
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device_index):
+    def __init__(self, device_index, period_ms=200):
         self.device_index = device_index
+        self.period_ms = period_ms
         self.proc = None
-        self.path = f"/tmp/tsu_bench_clocks_{os.getpid()}.csv"
+        self.path = f"/tmp/tsu_bench_clocks_{os.getpid()}_{id(self)}.csv"
 
     def start(self):
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200",
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", str(self.period_ms),
                  "-i", str(self.device_index)],
                 stdout=self.fh, stderr=subprocess.DEVNULL)
         except Exception:
@@ -168,6 +207,7 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
+            out["samples"] = len(sm)
             sm.sort()
             out["sm_mhz"] = sm[len(sm) // 2]
             out["sm_max_mhz"] = max(mx)
@@ -175,37 +215,265 @@ class ClockSampler:
         return out
 
 
-def measured_peak_gbs():
+def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
-        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md)"
-
-
-def profiled_traffic():
-    """dram bytes per half-sweep launch from the committed ncu capture of this workload, or None"""
-    p = os.path.join(ROOT, "profiles", "lattice_traffic.json")
-    try:
         d = json.load(open(p))
-        if d.get("workload") == WORKLOAD:
-            return float(d["dram_bytes_per_launch"])
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d["bf16_tflops_sustained"]), "source": "measured (MEASURED_PEAKS.json)"}
     except Exception:
-        pass
-    return None
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+                "source": "fallback (B200_PROFILING.md)"}
 
 
-def profiled_limiter():
-    """what the committed ncu capture says actually limits the kernel (the HBM fraction alone would mislead)"""
+def profiled_kernel():
+    """numbers of the committed ncu capture of the half-sweep kernel at this workload (profiles/lattice_kernel.json):
+    DRAM bytes per launch, executed instructions per 32-spin word and how many of them go through the integer
+    ALU / wide-multiply dispatch, which is what bounds the kernel"""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "lattice_traffic.json"))).get("limiter")
+        d = json.load(open(os.path.join(ROOT, "profiles", "lattice_kernel.json")))
+        return d if d.get("workload") == WORKLOAD else None
     except Exception:
         return None
 
 
+# ----------------------------------------------------------------------------- secondary configurations
+def _ev(torch):
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def _max_over_ranks(torch, dist, world, ms):
+    if world == 1:
+        return ms
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def tc_parity_probe(torch, Jd, T, seed, n_chains=8):
+    """the tensor-core sweep against a float64 torch evaluation of the reference's rule on the kernel's own trajectory
+    (h_i = J[i,:].s + b_i, accept iff u < sigmoid(h/T), gibbs.py:61-126): number of disagreeing sites and the
+    largest |u - p| among them.  One sweep of n_chains chains at the benchmark's matrix."""
+    from tsu_emulator_b200 import _lib
+
+    N = Jd.shape[0]
+    J64 = Jd.to(torch.float64)
+    st0 = (torch.rand(n_chains, N, device="cuda") < 0.5).to(torch.uint8)
+    st = st0.clone()
+    sweep0, chain0 = 77, 5
+    _lib.call("tsu_dense_gibbs_tc_run", _lib.ptr(Jd), None, _lib.ptr(st), n_chains, N, float(T), None, 1, seed, sweep0,
+              chain0, None, _lib.current_stream())
+    # the kernel's uniforms: 24 bits of word (site & 3) of Philox(counter = (site >> 2, chain, sweep, 'DENT'))
+    words = torch.empty((n_chains, N), dtype=torch.int64, device="cuda")
+    host = _lib.load()
+    import ctypes
+
+    for c in range(n_chains):
+        row = []
+        for g in range(N // 4):
+            ctr = (ctypes.c_uint32 * 4)(g, chain0 + c, sweep0, 0x44454E54)
+            key = (ctypes.c_uint32 * 2)(seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+            out = (ctypes.c_uint32 * 4)()
+            host.tsu_philox4x32_10_host(ctr, key, out)
+            row.extend(int(x) for x in out)
+        words[c] = torch.tensor(row, dtype=torch.int64)
+    u = (words >> 8).to(torch.float64) / 16777216.0
+    cur = st0.to(torch.float64)
+    after = st.to(torch.float64)
+    n_bad, max_eps = 0, 0.0
+    for i in range(N):
+        h = cur @ J64[i]
+        x = h / T
+        p = torch.where(x > 20, torch.ones_like(x), torch.where(x < -20, torch.zeros_like(x), 1.0 / (1.0 + torch.exp(-x))))
+        want = (u[:, i] < p).to(torch.float64)
+        bad = want != after[:, i]
+        if bool(bad.any()):
+            n_bad += int(bad.sum())
+            max_eps = max(max_eps, float((u[:, i] - p).abs()[bad].max()))
+        cur[:, i] = after[:, i]
+    return {"sites_checked": n_chains * N, "mismatches": n_bad, "max_eps": max_eps}
+
+
+def run_secondary(torch, dist, world, rank, local_rank, peaks):
+    import numpy as np
+
+    from tsu_emulator_b200 import (GibbsConfig, GibbsSampler, Ising2DEngine, IsingModel2D, QuadraticEnergy,
+                                   ThermalSamplingUnit, TSUConfig, _lib)
+    from tsu_emulator_b200.distributed import LatticeTempering, SlabShardedIsing2D
+
+    out = {}
+    sampler = ClockSampler(local_rank, period_ms=50)
+    if rank == 0:
+        sampler.start()
+
+    def guarded(name, fn):
+        try:
+            res = fn()
+            if res is not None:
+                out[name] = res
+        except Exception as exc:  # a secondary configuration must never take the primary line down
+            out[name] = {"error": repr(exc)}
+        torch.cuda.empty_cache()
+
+    # ---- C4: one 131072 x 131072 lattice as row slabs (strong), and 131072 rows per GPU (weak) -------------------
+    def c4(rows, cols, tag):
+        fac = lambda lr, r0: Ising2DEngine(lr, cols, temperature=TEMPERATURE, periodic=True, seed=1, row0=r0,
+                                           global_rows=rows).init_random()
+        drv = SlabShardedIsing2D(rows, cols, fac, periodic=True)
+        drv.sweep(3)
+        n_sw = 20
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = _ev(torch)
+        a.record()
+        drv.sweep(n_sw)
+        b.record()
+        torch.cuda.synchronize()
+        ms = _max_over_ranks(torch, dist, world, a.elapsed_time(b))
+        obs = drv.observables()
+        upd = float(rows) * cols * n_sw
+        ups = upd / ms * 1e3
+        return {"workload": f"2D Ising {rows}x{cols}, T=2.269, periodic, {world} row slab(s) of {rows // world} rows, "
+                            f"halo exchange per half-sweep ({'NCCL send/recv overlapped with the interior update' if world > 1 else 'local copy'}), {n_sw} sweeps",
+                "scaling": tag, "ms_per_sweep": ms / n_sw, "spin_updates_per_s": ups,
+                "hbm_frac_per_gpu": ups * BYTES_PER_UPDATE / world / (peaks["hbm_gbs"] * 1e9),
+                "energy_per_site": float(-(2.0 * rows * cols - 2.0 * obs[0, 1].item()) / (float(rows) * cols))}
+
+    guarded("C4_strong", lambda: c4(131072, 131072, "strong"))
+    if world > 1:
+        guarded("C4_weak", lambda: c4(131072 * world, 131072, "weak"))
+
+    # ---- C5a: 50 temperatures x K ladders x 1024^2 with replica exchange, ladders sharded over the ranks ----------
+    def c5_ladder():
+        temps = np.linspace(0.1, 5.0, 50)
+        K = 16 * world
+        fac = lambda n, r0, T: Ising2DEngine(1024, 1024, n_replicas=n, temperature=T, periodic=True, seed=5,
+                                             replica0=r0).init_random()
+        pt = LatticeTempering(temps, n_ladders=K, engine_factory=fac, n_sweeps=10, swap_interval=10, seed=9)
+        for _ in range(10):
+            pt.step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = _ev(torch)
+        a.record()
+        for _ in range(20):
+            pt.step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = _max_over_ranks(torch, dist, world, a.elapsed_time(b))
+        stats = pt.stats.cpu().numpy()
+        return {"workload": f"50 temperatures linspace(0.1, 5.0) x {K} ladders x 1024^2 periodic, 20 iterations x 10 sweeps, "
+                            f"exchange pass every 10 iterations ({'energies all-gathered over ' + str(world) + ' ranks' if world > 1 else 'one rank'})",
+                "scaling": "weak", "ms": ms, "spin_updates_per_s": 20.0 * 10 * K * 50 * 1024 * 1024 / ms * 1e3,
+                "swap_accept_rate": float(stats[1] / max(1, stats[0]))}
+
+    guarded("C5_ladder", c5_ladder)
+
+    if world == 1:
+        # ---- C1: IsingModel2D size=50, 1000 gibbs_update sweeps + magnetization + energy ---------------------------
+        def c1():
+            res = {}
+            for periodic in (True, False):
+                m = IsingModel2D(size=50, coupling=1.0, temperature=2.5, periodic=periodic, seed=0)
+                m.gibbs_update(10)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(1000):
+                    m.gibbs_update()
+                mag, en = m.magnetization(), m.energy()
+                dt = time.perf_counter() - t0
+                m2 = IsingModel2D(size=50, coupling=1.0, temperature=2.5, periodic=periodic, seed=0)
+                m2.gibbs_update(10)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                m2.gibbs_update(1000)
+                mag2, en2 = m2.magnetization(), m2.energy()
+                dt2 = time.perf_counter() - t0
+                res["periodic" if periodic else "open"] = {
+                    "wall_ms_1000_calls": dt * 1e3, "spin_updates_per_s": 2.5e6 / dt,
+                    "wall_ms_one_call_of_1000": dt2 * 1e3, "spin_updates_per_s_one_call": 2.5e6 / dt2,
+                    "same_state": bool(mag == mag2 and en == en2), "magnetization": float(mag), "energy": float(en)}
+            res["workload"] = ("IsingModel2D(size=50, coupling=1.0, temperature=2.5): 1000 gibbs_update() + magnetization() "
+                               "+ energy(), host wall clock (launch-latency bound: 2500 spins per sweep)")
+            return res
+
+        guarded("C1", c1)
+
+        # ---- C3: dense SK N=4096, 2048 chains, 10 sweeps on the tensor cores ------------------------------------------
+        def c3():
+            N, SW, seed = 4096, 10, 3
+            rng = np.random.default_rng(7)
+            J = rng.normal(size=(N, N)) / np.sqrt(N)
+            J = (J + J.T) / np.sqrt(2)
+            np.fill_diagonal(J, 0)
+            smp = GibbsSampler(GibbsConfig(temperature=1.0, n_sweeps=SW), seed=seed, precision="bf16")
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            st = smp.sample_chains(J, None, n_chains=2048, n_sweeps=SW, as_tensor=True)
+            torch.cuda.synchronize()
+            api_ms = (time.perf_counter() - t0) * 1e3
+            Jd = torch.from_numpy(J).cuda().to(torch.bfloat16).contiguous()
+            n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+            res = {"workload": f"GibbsSampler(precision='bf16') dense SK couplings (bf16) N={N}, sequential sweeps, tcgen05 + TMEM",
+                   "api_ms_2048_chains_10_sweeps_incl_J_upload": api_ms, "mean_bit": float(st.float().mean())}
+            for C, tag in ((2048, "2048_chains"), (128 * n_sm, "full_wave_%d_chains" % (128 * n_sm))):
+                s_ = (torch.rand(C, N, device="cuda") < 0.5).to(torch.uint8)
+                _lib.call("tsu_dense_gibbs_tc_run", _lib.ptr(Jd), None, _lib.ptr(s_), C, N, 1.0, None, 1, seed, 0, 0, None,
+                          _lib.current_stream())
+                best = 1e30
+                for _ in range(3):
+                    a, b = _ev(torch)
+                    a.record()
+                    _lib.call("tsu_dense_gibbs_tc_run", _lib.ptr(Jd), None, _lib.ptr(s_), C, N, 1.0, None, SW, seed, 1, 0,
+                              None, _lib.current_stream())
+                    b.record()
+                    torch.cuda.synchronize()
+                    best = min(best, a.elapsed_time(b))
+                flops = 2.0 * N * N * C * SW
+                res[tag] = {"ms": best, "spin_updates_per_s": C * N * SW / best * 1e3, "tflops": flops / best * 1e3 / 1e12,
+                            "roofline": {"bound": "tensor", "achieved": flops / best * 1e3 / 1e12,
+                                         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                         "frac": flops / best * 1e3 / 1e12 / peaks["bf16_tflops_sustained"],
+                                         "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed alone, but "
+                                                        "seconds of tensor work would settle there)"}}
+                del s_
+            res["parity"] = tc_parity_probe(torch, Jd, 1.0, seed)
+            return res
+
+        guarded("C3", c3)
+
+        # ---- C5b: Langevin 1e6 chains, dim 10 Gaussian, float64 (the reference's arithmetic) and float32 ----------------
+        def c5_langevin():
+            res = {"workload": "ThermalSamplingUnit.sample_from_energy(E = sum x^2, dim 10), 1e6 chains, 100 + 500 steps, dt 0.01"}
+            for dtype in ("float64", "float32"):
+                tsu = ThermalSamplingUnit(TSUConfig(temperature=1.0, dt=0.01, friction=1.0, n_burnin=100, n_steps=500),
+                                          seed=1, dtype=dtype)
+                tsu.sample_from_energy(QuadraticEnergy(), np.zeros(10), 1000, as_tensor=True)
+                torch.cuda.synchronize()
+                ms = 1e30
+                for _ in range(2):
+                    a, b = _ev(torch)
+                    a.record()
+                    x = tsu.sample_from_energy(QuadraticEnergy(), np.zeros(10), 1_000_000, as_tensor=True)
+                    b.record()
+                    torch.cuda.synchronize()
+                    ms = min(ms, a.elapsed_time(b))
+                res[dtype] = {"ms": ms, "chain_steps_per_s": 1e6 * 600 / ms * 1e3, "coordinate_updates_per_s": 1e6 * 6000 / ms * 1e3,
+                              "variance": float(x.var()), "euler_maruyama_theory": 0.5 / (1 - 0.01)}
+            return res
+
+        guarded("C5_langevin", c5_langevin)
+
+    if rank == 0:
+        out["clocks"] = sampler.stop()
+        out["clocks"]["note"] = "nvidia-smi sampled every 50 ms over all secondary configurations of this run"
+    return out
+
+
 # ----------------------------------------------------------------------------- B200 arm
 def run_b200_arm(args):
-    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -230,9 +498,12 @@ def run_b200_arm(args):
             n_words = (os.cpu_count() + 63) // 64
             words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
             cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1} & cpu_mask0
-            if cpus:
+            if cpus and cpus != cpu_mask0:
                 os.sched_setaffinity(0, cpus)
-                numa_note = f"rank pinned to the {len(cpus)} CPU cores local to its GPU"
+                numa_note = f"rank pinned to the {len(cpus)} CPU cores NVML reports as local to its GPU"
+            else:
+                numa_note = (f"NVML reports the same {len(cpu_mask0)} CPU cores as local to every GPU (one NUMA node visible): "
+                             "nothing to bind")
         except Exception as exc:  # no NVML / no permission: keep the inherited mask
             numa_note = f"cpu affinity unchanged ({type(exc).__name__})"
     json_fd = None
@@ -245,6 +516,7 @@ def run_b200_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_rep = args.replicas
     size = args.size
+    peaks = measured_peaks()
 
     def barrier():
         if world > 1:
@@ -271,33 +543,30 @@ def run_b200_arm(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = _max_over_ranks(torch, dist, world, ms)
     n_launches = args.steps * SWEEPS_PER_STEP * 2
     value = world * updates_per_step * args.steps / (ms * 1e-3)
     launch_s = ms * 1e-3 / n_launches
     alg_bytes_per_launch = BYTES_PER_UPDATE * n_rep * size * size / 2
-    peak, peak_src = measured_peak_gbs()
     achieved = alg_bytes_per_launch / launch_s / 1e9
 
     # ---- end to end through the host API: pinned host lattices -> sweeps -> observables -----
     state_bytes = eng.state.numel() * 4
-    chunk = max(1, n_rep // 16)
+    n_chunks = 16
+    chunk = max(1, n_rep // n_chunks)
     e2e = None
     try:
         # pinned host source: the full 34.4 GB state at N = 1; with N ranks sharing one host the buffer is capped
-        # (host RAM / N) and its chunks are re-used round-robin as the source of the 16 per-step uploads - every
+        # (host RAM / N) and its chunks are re-used round-robin as the source of the per-step uploads - every
         # step still copies state_bytes from pinned host memory to the device
-        host_chunks = 16 if world == 1 else max(1, 16 // world)
+        host_chunks = n_chunks if world == 1 else max(1, n_chunks // world)
         host = torch.empty((host_chunks * chunk,) + tuple(eng.state.shape[1:]), dtype=torch.int32, pin_memory=True)
         host.copy_(eng.state[: host_chunks * chunk])  # synthetic input lattices (any valid packed configuration)
         obs_host = torch.empty((n_rep, 2), dtype=torch.int64, pin_memory=True)
         copy_stream = torch.cuda.Stream()
         main = torch.cuda.current_stream()
 
-        def e2e_step():
+        def upload(record_events):
             evs = []
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_stream(main)
@@ -305,9 +574,14 @@ def run_b200_arm(args):
                     n_c = min(chunk, n_rep - c0)
                     h0 = (k % host_chunks) * chunk
                     eng.state[c0:c0 + n_c].copy_(host[h0:h0 + n_c], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(copy_stream)
-                    evs.append(ev)
+                    if record_events:
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                        evs.append(ev)
+            return evs
+
+        def e2e_step():
+            evs = upload(True)
             # sweeps of chunk k overlap the upload of chunk k+1
             for k, c0 in enumerate(range(0, n_rep, chunk)):
                 main.wait_event(evs[k])
@@ -327,24 +601,41 @@ def run_b200_arm(args):
             e2e_step()
         e1.record()
         barrier()
-        e2e_ms = e0.elapsed_time(e1)
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+        e2e_ms = _max_over_ranks(torch, dist, world, e0.elapsed_time(e1))
+        # the upload alone, all ranks at the same time: what the host (DRAM + PCIe) can deliver to N GPUs at once
+        barrier()
+        c0_, c1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0_.record()
+        for _ in range(2):
+            upload(False)
+            main.wait_stream(copy_stream)
+        c1_.record()
+        barrier()
+        h2d_ms = _max_over_ranks(torch, dist, world, c0_.elapsed_time(c1_)) / 2
         e2e = {
             "value": world * updates_per_step * args.steps / (e2e_ms * 1e-3),
             "unit": UNIT,
             "h2d_bytes_per_step": int(state_bytes) * world,
             "d2h_bytes_per_step": int(n_rep * 16) * world,
             "ms_per_step": e2e_ms / args.steps,
-            "api": "Ising2DEngine: pinned host state -> H2D (16 chunks, overlapped) -> sweep(10) -> observables -> D2H",
+            "api": f"Ising2DEngine: pinned host state -> H2D ({n_chunks} chunks, overlapped) -> sweep(10) -> observables -> D2H",
             "pinned_host_bytes": int(host.numel() * 4),
             "host_affinity": numa_note,
+            "h2d_only": {"ms_per_step": h2d_ms, "gbs_per_gpu": state_bytes / h2d_ms / 1e6,
+                         "gbs_all_gpus": state_bytes * world / h2d_ms / 1e6,
+                         "note": "the same uploads without the sweeps, all ranks at once: an end-to-end step cannot be "
+                                 "shorter than max(this, the device-resident step)"},
         }
         del host
     except Exception as exc:  # e.g. pinned allocation refused
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(exc)}
+
+    jit_on = getattr(eng, "_jit", 0) > 0
+    del eng
+    torch.cuda.empty_cache()
+    secondary = None
+    if not args.no_secondary:
+        secondary = run_secondary(torch, dist, world, rank, local_rank, peaks)
 
     cpu = None
     if cpu_mask0 is not None:
@@ -356,6 +647,20 @@ def run_b200_arm(args):
         dist.destroy_process_group()
     if rank != 0:
         return
+    prof = profiled_kernel()
+    math_issue = None
+    if prof and clocks and clocks.get("sm_mhz"):
+        # B200 issues LOP3 / SHF / IADD3 and IMAD.WIDE at one warp instruction per 2 cycles per SM sub-partition, and the
+        # two do NOT overlap (tools/microbench/pipes.cu): a word costs 2 cycles per such instruction at best
+        slots = prof["alu_instr_per_word"] + prof["wide_mul_instr_per_word"]
+        words_per_s = value / world / 32.0
+        cap_words = 148 * 4 * clocks["sm_mhz"] * 1e6 / (2.0 * slots) * 32
+        math_issue = {"alu_instr_per_word": prof["alu_instr_per_word"], "wide_mul_instr_per_word": prof["wide_mul_instr_per_word"],
+                      "instr_per_word": prof["instr_per_word"], "cycles_per_slot": 2.0,
+                      "frac": words_per_s / cap_words,
+                      "note": "fraction of the integer-ALU + wide-multiply dispatch slots (148 SMs x 4 sub-partitions x "
+                              "1 warp instruction per 2 cycles at the sampled SM clock) this kernel's executed instruction "
+                              "mix occupies; counts from the committed ncu capture (" + prof.get("source", "profiles/") + ")"}
     line = {
         "metric": METRIC,
         "value": value,
@@ -382,21 +687,23 @@ def run_b200_arm(args):
         "roofline": {
             "bound": "hbm",
             "achieved": achieved,
-            "peak": peak,
+            "peak": peaks["hbm_gbs"],
             "unit": "GB/s",
-            "frac": achieved / peak,
-            "traffic": profiled_traffic(),
-            "peak_source": peak_src,
+            "frac": achieved / peaks["hbm_gbs"],
+            "traffic": prof.get("dram_bytes_per_launch") if prof else None,
+            "traffic_source": (prof.get("source") if prof else None),
+            "peak_source": peaks["source"] + " hbm_gbs",
             "kernel": ("tsu_jit_half_sweep (NVRTC specialisation of half_sweep_fast_body for this temperature)"
-                       if getattr(eng, "_jit", 0) > 0 else "half_sweep_fast_kernel"),
+                       if jit_on else "half_sweep_fast_kernel"),
             "algorithmic_bytes_per_launch": alg_bytes_per_launch,
             "launch_ms": launch_s * 1e3,
-            "measured_limiter": profiled_limiter(),
+            "math_issue": math_issue,
         },
         "cpu_baseline": cpu,
         "e2e": e2e,
         "gpu_launches": n_launches,
         "clocks": clocks,
+        "secondary": secondary,
     }
     if json_fd is not None:
         sys.stdout.flush()
@@ -415,6 +722,7 @@ def main():
     ap.add_argument("--replicas", type=int, default=N_REPLICAS, help="replicas per GPU (default = the named workload)")
     ap.add_argument("--size", type=int, default=L)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configurations")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "b200" else args.warmup

@@ -1,13 +1,15 @@
 """
-ORACLE support (test infrastructure): import the UNMODIFIED reference modules from
-/root/reference when that tree exists (build container only - it is absent on the GPU box).
+ORACLE support (test infrastructure): import the UNMODIFIED reference modules from /root/reference when that
+tree exists (build container), else from the byte-for-byte copy oracle/make_ref.py placed under oracle/_ref/
+(git-ignored; it travels to the GPU box, where /root/reference is absent).
 
 tsu/gibbs.py and tsu/core.py import only numpy + stdlib, so they are loaded by file path.
 tsu/models/ising.py imports matplotlib at module scope (ising.py:20-21); matplotlib is not
 installed here, so empty stand-in modules are registered in sys.modules first (nothing in the
 hot path touches them).
 
-Nothing under tests -m gpu, smoke() or bench.py may call this at run time.
+Used by the CPU tests, by `bench.py --impl reference` / the cpu_baseline leg (the reference timed on the host
+cores) and by tests/test_reference_suite.py; never by the product package.
 """
 
 import importlib.util
@@ -19,7 +21,9 @@ from unittest import mock
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("TSU_REFERENCE_ROOT", "/root/reference")
+from .make_ref import ref_root
+
+REFERENCE_ROOT = os.environ.get("TSU_REFERENCE_ROOT") or ref_root() or "/root/reference"
 
 
 def reference_available() -> bool:

@@ -1,0 +1,104 @@
+"""the reference's OWN acceptance tests and benchmark drivers, unmodified, running on the B200 engine.
+
+`tsu_emulator_b200/compat` holds an import shim (`tsu.gibbs`, `tsu.models`, `tsu.core`); with it first on the
+path, `from tsu.gibbs import GibbsSampler` in the reference's tests/test_{gibbs,ising,core}.py and in
+tsu/benchmarks/{sampling,comparison,optimization}.py resolves to this package.  The reference files come
+byte-for-byte from oracle/_ref (python -m oracle.make_ref; /root/reference itself in the build container)."""
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+import types
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "tsu_emulator_b200", "compat")
+
+
+def _ref_root():
+    from oracle import make_ref
+
+    root = make_ref.ref_root()
+    if root is None:
+        pytest.skip("no reference tree (neither /root/reference nor oracle/_ref)")
+    return root
+
+
+# Reference tests that cannot pass for reasons that are not the engine's:
+#   test_gaussian_validation  fails in the reference itself with the installed scipy (kstest(args=(mu, sigma)) -> ndtr
+#                             TypeError, tsu/core.py:315); the shim reports the same statistics through
+#                             scipy.stats.norm(...).cdf and passes, so nothing is deselected today - kept as a note.
+DESELECT = []
+
+
+def test_reference_test_files_pass_on_the_b200_engine(tmp_path):
+    ref = _ref_root()
+    files = [os.path.join(ref, "tests", f) for f in ("test_gibbs.py", "test_ising.py", "test_core.py")]
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([SHIM, ROOT, env.get("PYTHONPATH", "")])
+    cmd = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "--rootdir", str(tmp_path), "-x",
+           "-o", "addopts=", *files]
+    for d in DESELECT:
+        cmd += ["--deselect", d]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=str(tmp_path), timeout=1500)
+    tail = (r.stdout or "")[-3000:] + (r.stderr or "")[-1500:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and " failed" not in r.stdout, tail
+    print(r.stdout.strip().splitlines()[-1])
+
+
+def _load_reference_benchmarks(ref):
+    """tsu.benchmarks.{sampling,comparison,optimization} of the reference as sub-modules of the SHIM's `tsu` package
+    (their `from ..gibbs import GibbsSampler, GibbsConfig` then binds the B200 sampler); the reference's own
+    tsu/benchmarks/__init__.py is not used because it also imports the ML / runner modules"""
+    if SHIM not in sys.path:
+        sys.path.insert(0, SHIM)
+    import tsu  # the shim
+
+    assert os.path.realpath(os.path.dirname(tsu.__file__)).startswith(os.path.realpath(SHIM))
+    pkg = types.ModuleType("tsu.benchmarks")
+    pkg.__path__ = [os.path.join(ref, "tsu", "benchmarks")]
+    pkg.__package__ = "tsu.benchmarks"
+    sys.modules["tsu.benchmarks"] = pkg
+    mods = {}
+    for name in ("sampling", "comparison", "optimization"):
+        spec = importlib.util.spec_from_file_location(f"tsu.benchmarks.{name}", os.path.join(ref, "tsu", "benchmarks", name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[spec.name] = mod
+        spec.loader.exec_module(mod)
+        mods[name] = mod
+    return mods
+
+
+def test_reference_benchmark_drivers_run_on_the_b200_engine(capsys):
+    """SamplingBenchmark / ComparisonBenchmark / OptimizationBenchmark in quick mode (tsu/benchmarks/sampling.py:130,
+    197,254; comparison.py:120,198; optimization.py:151,273 call sample_boltzmann / simulated_annealing)"""
+    import tsu_emulator_b200
+
+    ref = _ref_root()
+    mods = _load_reference_benchmarks(ref)
+    assert mods["sampling"].GibbsSampler is tsu_emulator_b200.GibbsSampler
+    res = mods["sampling"].SamplingBenchmark(seed=42).run_all_benchmarks(quick=True)
+    assert len(res) >= 3
+    summary = {}
+    for name, r in res.items():
+        s = r.summary()
+        summary[name] = s
+        assert s["n_trials"] >= 1 if "n_trials" in s else True
+    opt = mods["optimization"].OptimizationBenchmark(seed=42).run_all_benchmarks(quick=True)
+    assert len(opt) >= 2
+    cmp_ = mods["comparison"].ComparisonBenchmark(seed=42).run_all_comparisons(quick=True)
+    assert len(cmp_) >= 1
+    out = capsys.readouterr().out
+    with capsys.disabled():
+        print("reference benchmark drivers on the B200 engine (quick mode):")
+        for name, s in summary.items():
+            thr = s.get("throughput_samples_per_sec", {}).get("mean")
+            kl = s.get("kl_divergence", {}).get("mean")
+            print(f"   {name}: {s.get('n_samples')} samples x {s.get('n_trials')} trials, "
+                  f"{thr:.4g} samples/s, KL {kl:.4g}" if thr is not None else f"   {name}: {json.dumps(s, default=str)[:200]}")
+    assert "Error" not in out and "Traceback" not in out
