@@ -316,10 +316,10 @@ def run_secondary(torch, dist, world, rank, local_rank, peaks):
         torch.cuda.empty_cache()
 
     # ---- C4: one 131072 x 131072 lattice as row slabs (strong), and 131072 rows per GPU (weak) -------------------
-    def c4(rows, cols, tag):
+    def c4(rows, cols, tag, transport="auto"):
         fac = lambda lr, r0: Ising2DEngine(lr, cols, temperature=TEMPERATURE, periodic=True, seed=1, row0=r0,
                                            global_rows=rows).init_random()
-        drv = SlabShardedIsing2D(rows, cols, fac, periodic=True)
+        drv = SlabShardedIsing2D(rows, cols, fac, periodic=True, transport=transport)
         drv.sweep(3)
         n_sw = 20
         torch.cuda.synchronize()
@@ -332,10 +332,16 @@ def run_secondary(torch, dist, world, rank, local_rank, peaks):
         torch.cuda.synchronize()
         ms = _max_over_ranks(torch, dist, world, a.elapsed_time(b))
         obs = drv.observables()
+        kind = drv.transport()
+        how = {"p2p": "boundary rows written into the neighbours' peer-mapped halo buffers over NVLink, one C-ABI call per "
+                      "sweep batch, overlapped with the interior update",
+               "nccl": "NCCL send/recv on a side stream, overlapped with the interior update",
+               "local": "local copy"}[kind]
+        drv.close()
         upd = float(rows) * cols * n_sw
         ups = upd / ms * 1e3
         return {"workload": f"2D Ising {rows}x{cols}, T=2.269, periodic, {world} row slab(s) of {rows // world} rows, "
-                            f"halo exchange per half-sweep ({'NCCL send/recv overlapped with the interior update' if world > 1 else 'local copy'}), {n_sw} sweeps",
+                            f"halo exchange per half-sweep ({how}), {n_sw} sweeps", "transport": kind,
                 "scaling": tag, "ms_per_sweep": ms / n_sw, "spin_updates_per_s": ups,
                 "hbm_frac_per_gpu": ups * BYTES_PER_UPDATE / world / (peaks["hbm_gbs"] * 1e9),
                 "energy_per_site": float(-(2.0 * rows * cols - 2.0 * obs[0, 1].item()) / (float(rows) * cols))}
@@ -343,6 +349,7 @@ def run_secondary(torch, dist, world, rank, local_rank, peaks):
     guarded("C4_strong", lambda: c4(131072, 131072, "strong"))
     if world > 1:
         guarded("C4_weak", lambda: c4(131072 * world, 131072, "weak"))
+        guarded("C4_strong_nccl", lambda: c4(131072, 131072, "strong", transport="nccl"))
 
     # ---- C5a: 50 temperatures x K ladders x 1024^2 with replica exchange, ladders sharded over the ranks ----------
     def c5_ladder():

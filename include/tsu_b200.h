@@ -47,6 +47,19 @@ void tsu_philox4x32_10_host(const uint32_t ctr[4], const uint32_t key[2], uint32
 /* d_out[i] = word (i&3) of Philox(counter=(i>>2 lo, i>>2 hi, offset lo, 'FILL'), key=seed) */
 int tsu_philox_fill_u32(uint32_t* d_out, uint64_t n, uint64_t seed, uint32_t offset, uintptr_t stream);
 
+/* ------------------------------------------------------------------ peer-mapped buffers */
+/* Device buffers that other processes of the same box can map (CUDA IPC over NVLink): the halo rows of the
+ * row-slab driver are written straight into the neighbour's buffer.  tsu_peer_alloc is the one place where the
+ * library allocates device memory (zero-filled cudaMalloc: pooled / virtual-memory allocations cannot be exported);
+ * the owner frees it with tsu_peer_free after every peer has closed its mapping. */
+int tsu_peer_alloc(void** d_ptr, size_t bytes);
+int tsu_peer_free(void* d_ptr);
+int tsu_peer_get_handle(void* d_ptr, unsigned char handle[64]);
+int tsu_peer_open_handle(const unsigned char handle[64], void** d_ptr);
+int tsu_peer_close_handle(void* d_ptr);
+/* one word of such a buffer to the host (synchronising copy; status words) */
+int tsu_peer_read_u32(const void* d_ptr, uint32_t* h_out);
+
 /* ------------------------------------------------------------------ 2-D lattice ------- */
 /* The lattice kernels read their tuning knobs (TSU_LATTICE_STRIP, TSU_LATTICE_W, TSU_LATTICE_RESIDENT,
  * TSU_LATTICE_OPEN_GENERIC, TSU_LATTICE_OBS_GENERIC, TSU_JIT_W, TSU_JIT_MINB, TSU_JIT_UNROLL: launch shapes and
@@ -102,6 +115,24 @@ int tsu_ising2d_half_sweep_rows(int jit_handle, uint32_t* d_state, int n_replica
                                 const int32_t* d_lut_index, uint64_t seed, uint32_t sweep,
                                 uint32_t replica0, int row0, const uint32_t* d_halo_top,
                                 const uint32_t* d_halo_bot, int row_begin, int row_end, uintptr_t stream);
+/* n_sweeps sweeps of ONE row slab of a lattice that is split over the GPUs of a box, halo exchange included: the
+ * compute step and its exchange in one call, no collective library in the data path.  Per half-sweep
+ *   side stream: wait for the neighbours' rows of the other colour -> update rows 0 and rows-1 -> copy them into
+ *                the neighbours' halo buffers (peer-mapped pointers, NVLink) -> publish the message number
+ *   main stream: update rows 1 .. rows-2 meanwhile (they need no halo)
+ * d_halo [2 colours][2: above / below][n_replicas][wpr] and d_flags [>= 9 words: 2 x 2 arrival counters, word 8 =
+ * status, set to 1 if a neighbour's rows did not arrive within ~20 s] are this rank's buffers (tsu_peer_alloc);
+ * d_up_* / d_down_* are the mapped buffers of the ranks holding the rows above / below (NULL = open edge).
+ * msgs_colour0/1: messages already exchanged per colour before this call (every rank passes the same numbers; the
+ * call exchanges n_sweeps of colour 0 and n_sweeps + 1 of colour 1).  rows >= 4.  Bits are identical to the
+ * unsharded lattice (global-row Philox counters). */
+int tsu_ising2d_slab_sweeps_p2p(int jit_handle, uint32_t* d_state, int n_replicas, int rows, int cols,
+                                int wrap_cols, const uint32_t* d_lut, const int32_t* d_lut_index,
+                                uint64_t seed, uint32_t sweep0, int n_sweeps, uint32_t replica0, int row0,
+                                uint32_t* d_halo, uint32_t* d_flags, uint32_t* d_up_halo,
+                                uint32_t* d_up_flags, uint32_t* d_down_halo, uint32_t* d_down_flags,
+                                uint32_t msgs_colour0, uint32_t msgs_colour1, uintptr_t main_stream,
+                                uintptr_t side_stream);
 /* n_sweeps full sweeps (black then white), sweep indices sweep0 .. sweep0+n_sweeps-1, no halos.
  * Two launches per sweep; lattices of at most 4096 words per replica in batches that would not fill the GPU
  * (BASELINE config 1: 50 x 50) run ALL sweeps of the call in ONE launch, one thread block per replica.  Same

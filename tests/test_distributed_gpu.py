@@ -93,21 +93,32 @@ def _slab_rank(rank, world, port, rows, cols, q):
     from tsu_emulator_b200.distributed import SlabShardedIsing2D
 
     ok = True
-    for overlap in (True, False):
-        fac = lambda lr, r0: Ising2DEngine(lr, cols, temperature=2.269, periodic=True, seed=7, row0=r0, global_rows=rows).init_random()
-        drv = SlabShardedIsing2D(rows, cols, fac, periodic=True, overlap=overlap).sweep(2).sweep(1)
-        whole = Ising2DEngine(rows, cols, temperature=2.269, periodic=True, seed=7).init_random().sweep(3)
-        lr = rows // world
-        ok = ok and torch.equal(drv.engine.state[0], whole.state[0][:, rank * lr:(rank + 1) * lr, :])
+    whole = Ising2DEngine(rows, cols, n_replicas=2, temperature=2.269, periodic=True, seed=7).init_random().sweep(3)
+    lr = rows // world
+    for overlap, transport in ((True, "p2p"), (True, "nccl"), (False, "nccl")):
+        fac = lambda lr_, r0: Ising2DEngine(lr_, cols, n_replicas=2, temperature=2.269, periodic=True, seed=7, row0=r0,
+                                            global_rows=rows).init_random()
+        drv = SlabShardedIsing2D(rows, cols, fac, periodic=True, overlap=overlap, transport=transport)
+        ok = ok and drv.transport() == transport
+        drv.sweep(2).sweep(1)
+        ok = ok and torch.equal(drv.engine.state, whole.state[:, :, rank * lr:(rank + 1) * lr, :])
         ok = ok and torch.equal(drv.observables(), whole.observables_tensor())
+        drv.close()
+    # open boundaries: the first and the last rank have one neighbour only
+    whole = Ising2DEngine(rows, cols, temperature=2.0, periodic=False, seed=8).init_random().sweep(2)
+    fac = lambda lr_, r0: Ising2DEngine(lr_, cols, temperature=2.0, periodic=False, seed=8, row0=r0, global_rows=rows).init_random()
+    drv = SlabShardedIsing2D(rows, cols, fac, periodic=False, transport="p2p").sweep(2)
+    ok = ok and torch.equal(drv.engine.state, whole.state[:, :, rank * lr:(rank + 1) * lr, :])
+    drv.close()
     q.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()
 
 
 def test_row_slabs_on_all_gpus_match_single_gpu():
-    """one NCCL rank per visible GPU (skipped on a one-GPU box): overlapped and serial halo exchange give the bits and
-    the observables of the unsharded lattice"""
+    """one rank per visible GPU (skipped on a one-GPU box): peer-mapped halos (one C-ABI call per sweep batch), NCCL
+    send/recv overlapped with the interior update and the serial exchange all give the bits and the observables of the
+    unsharded lattice, periodic and open"""
     import torch
     import torch.multiprocessing as mp
     world = torch.cuda.device_count()

@@ -35,6 +35,12 @@ SIGNATURES = {
     "tsu_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "tsu_philox4x32_10_host": (None, [POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint32)]),
     "tsu_philox_fill_u32": (c_int, [c_void_p, c_uint64, c_uint64, c_uint32, c_uintptr]),
+    "tsu_peer_alloc": (c_int, [POINTER(c_void_p), ctypes.c_size_t]),
+    "tsu_peer_free": (c_int, [c_void_p]),
+    "tsu_peer_get_handle": (c_int, [c_void_p, c_char_p]),
+    "tsu_peer_open_handle": (c_int, [c_char_p, POINTER(c_void_p)]),
+    "tsu_peer_close_handle": (c_int, [c_void_p]),
+    "tsu_peer_read_u32": (c_int, [c_void_p, POINTER(c_uint32)]),
     "tsu_ising2d_reload_tuning": (None, []),
     "tsu_ising2d_words_per_row": (c_int64, [c_int]),
     "tsu_ising2d_state_words": (c_int64, [c_int, c_int]),
@@ -50,6 +56,11 @@ SIGNATURES = {
         c_int,
         [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_uint64, c_uint32, c_uint32,
          c_int, c_void_p, c_void_p, c_int, c_int, c_uintptr],
+    ),
+    "tsu_ising2d_slab_sweeps_p2p": (
+        c_int,
+        [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_uint64, c_uint32, c_int, c_uint32, c_int,
+         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_uint32, c_uintptr, c_uintptr],
     ),
     "tsu_ising2d_sweeps": (
         c_int,

@@ -1,4 +1,6 @@
 // Library-level entry points: version, error strings, device probe, Philox helpers.
+#include <cstring>
+
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -54,6 +56,49 @@ void tsu_philox4x32_10_host(const uint32_t ctr[4], const uint32_t key[2], uint32
   out[1] = o.y;
   out[2] = o.z;
   out[3] = o.w;
+}
+
+// ---- device buffers other ranks of the box can map (CUDA IPC): halos of the row-slab driver ----------------
+int tsu_peer_alloc(void** d_ptr, size_t bytes) {
+  TSU_CHECK_ARG(d_ptr && bytes > 0);
+  cudaError_t e = cudaMalloc(d_ptr, bytes);  // plain cudaMalloc: pool / VMM allocations cannot be exported
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemset(*d_ptr, 0, bytes);
+  return e == cudaSuccess ? TSU_OK : (int)e;
+}
+
+int tsu_peer_free(void* d_ptr) {
+  cudaError_t e = cudaFree(d_ptr);
+  return e == cudaSuccess ? TSU_OK : (int)e;
+}
+
+int tsu_peer_get_handle(void* d_ptr, unsigned char handle[64]) {
+  TSU_CHECK_ARG(d_ptr && handle);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, d_ptr);
+  if (e != cudaSuccess) return (int)e;
+  memcpy(handle, &h, 64);
+  return TSU_OK;
+}
+
+int tsu_peer_open_handle(const unsigned char handle[64], void** d_ptr) {
+  TSU_CHECK_ARG(handle && d_ptr);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  return e == cudaSuccess ? TSU_OK : (int)e;
+}
+
+int tsu_peer_read_u32(const void* d_ptr, uint32_t* h_out) {
+  TSU_CHECK_ARG(d_ptr && h_out);
+  cudaError_t e = cudaMemcpy(h_out, d_ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost);  // synchronises
+  return e == cudaSuccess ? TSU_OK : (int)e;
+}
+
+int tsu_peer_close_handle(void* d_ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(d_ptr);
+  return e == cudaSuccess ? TSU_OK : (int)e;
 }
 
 int tsu_philox_fill_u32(uint32_t* d_out, uint64_t n, uint64_t seed, uint32_t offset, uintptr_t stream) {

@@ -511,6 +511,51 @@ __global__ void energy_from_obs_kernel(const unsigned long long* __restrict__ ob
   energy[r] = -J * ((double)n_bonds - 2.0 * anti) - h * (2.0 * up - (double)n_sites);
 }
 
+// ---- row slabs with peer-mapped halos (tsu_ising2d_slab_sweeps_p2p) ---------------------------------------
+// copy one row of `colour` of every replica into a halo buffer that may live on another GPU (NVLink peer mapping)
+__global__ void __launch_bounds__(256) slab_send_rows_kernel(const uint32_t* __restrict__ state, int n_replicas, int rows,
+                                                           int wpr, int colour, uint32_t* up_dst, uint32_t* down_dst) {
+  // up_dst   <- my first row (the row below the upper neighbour's last row)
+  // down_dst <- my last row  (the row above the lower neighbour's first row)
+  const int nvec = wpr >> 2;
+  const long long per_side = (long long)n_replicas * nvec;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < 2 * per_side; t += (long long)gridDim.x * blockDim.x) {
+    const int side = t >= per_side;
+    uint32_t* dst = side ? down_dst : up_dst;
+    if (!dst) continue;
+    const long long u = t - side * per_side;
+    const int rep = (int)(u / nvec), v = (int)(u - (long long)rep * nvec);
+    const size_t row = side ? (size_t)(rows - 1) : 0;
+    const uint4 x = *reinterpret_cast<const uint4*>(state + (((size_t)rep * 2 + colour) * rows + row) * wpr + 4 * v);
+    *reinterpret_cast<uint4*>(dst + (size_t)rep * wpr + 4 * v) = x;
+  }
+}
+
+// the rows sent before this kernel (stream order) are complete: publish their message number to the receivers
+__global__ void slab_signal_kernel(uint32_t* up_flag, uint32_t* down_flag, uint32_t value) {
+  __threadfence_system();
+  if (up_flag) *reinterpret_cast<volatile uint32_t*>(up_flag) = value;
+  if (down_flag) *reinterpret_cast<volatile uint32_t*>(down_flag) = value;
+}
+
+// hold the stream until both neighbours' rows with message number >= need have arrived (they write the counters
+// through their peer mapping).  Gives up after ~20 s and raises the status word instead of hanging the GPU.
+__global__ void slab_wait_kernel(const uint32_t* flag_a, const uint32_t* flag_b, uint32_t need, uint32_t* status) {
+  const long long t0 = clock64();
+  const volatile uint32_t* fa = flag_a;
+  const volatile uint32_t* fb = flag_b;
+  while (true) {
+    const bool a_ok = !fa || (int32_t)(*fa - need) >= 0;
+    const bool b_ok = !fb || (int32_t)(*fb - need) >= 0;
+    if (a_ok && b_ok) return;
+    if (clock64() - t0 > 40000000000LL) {
+      *status = 1u;
+      return;
+    }
+    __nanosleep(200);
+  }
+}
+
 bool geom_ok(int n_replicas, int rows, int cols) {
   // counter word 1 of the lattice stream keeps the global row in 24 bits, counter word 0 the 4-word group in 24
   return n_replicas > 0 && rows > 0 && cols > 0 && cols < (1 << 26) && rows <= TSU_LATTICE_MAX_ROWS;
@@ -792,6 +837,83 @@ int tsu_ising2d_half_sweep_rows(int jit_handle, uint32_t* d_state, int n_replica
   const JitKernel jit = (jit_handle > 0 && !d_lut_index) ? jit_function(jit_handle) : JitKernel{nullptr, 0};
   return launch_half_sweep(d_state, n_replicas, rows, cols, wrap_rows, wrap_cols, colour, d_lut, d_lut_index, seed, sweep,
                            replica0, row0, d_halo_top, d_halo_bot, tsu_stream(stream), jit, row_begin, row_end);
+}
+
+int tsu_ising2d_slab_sweeps_p2p(int jit_handle, uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_cols,
+                                const uint32_t* d_lut, const int32_t* d_lut_index, uint64_t seed, uint32_t sweep0,
+                                int n_sweeps, uint32_t replica0, int row0, uint32_t* d_halo, uint32_t* d_flags,
+                                uint32_t* d_up_halo, uint32_t* d_up_flags, uint32_t* d_down_halo, uint32_t* d_down_flags,
+                                uint32_t msgs_colour0, uint32_t msgs_colour1, uintptr_t main_stream,
+                                uintptr_t side_stream) {
+  TSU_CHECK_ARG(d_state && d_lut && d_halo && d_flags && geom_ok(n_replicas, rows, cols) && rows_ok(rows, row0));
+  TSU_CHECK_ARG(rows >= 4 && n_sweeps >= 0 && main_stream != side_stream);
+  TSU_CHECK_ARG(!wrap_cols || (cols % 2 == 0 && cols > 2));
+  TSU_CHECK_ARG((d_up_halo == nullptr) == (d_up_flags == nullptr) && (d_down_halo == nullptr) == (d_down_flags == nullptr));
+  const JitKernel jit = (jit_handle > 0 && !d_lut_index) ? jit_function(jit_handle) : JitKernel{nullptr, 0};
+  cudaStream_t main = tsu_stream(main_stream), side = tsu_stream(side_stream);
+  const int wpr = words_per_row(cols);
+  const size_t side_words = (size_t)n_replicas * wpr;  // one halo row set
+  auto halo = [&](uint32_t* base, int colour, int which) { return base ? base + ((size_t)colour * 2 + which) * side_words : nullptr; };
+  auto flag = [&](uint32_t* base, int colour, int which) { return base ? base + colour * 2 + which : nullptr; };
+  uint32_t msgs[2] = {msgs_colour0, msgs_colour1};
+  cudaEvent_t ev_int[2], ev_bnd[2], ev_join;
+  for (int k = 0; k < 2; ++k) {
+    if (cudaEventCreateWithFlags(&ev_int[k], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev_bnd[k], cudaEventDisableTiming) != cudaSuccess)
+      return (int)cudaGetLastError();
+  }
+  if (cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) return (int)cudaGetLastError();
+  const unsigned send_grid = blocks_for(2LL * n_replicas * (wpr / 4), 256) < 64u ? blocks_for(2LL * n_replicas * (wpr / 4), 256) : 64u;
+  // what a half-sweep of `colour` sends afterwards: my first row to the rank above (its "below" halo), my last row
+  // to the rank below (its "above" halo), then the message number
+  auto send = [&](int colour) {
+    ++msgs[colour];
+    slab_send_rows_kernel<<<send_grid, 256, 0, side>>>(d_state, n_replicas, rows, wpr, colour, halo(d_up_halo, colour, 1),
+                                                      halo(d_down_halo, colour, 0));
+    slab_signal_kernel<<<1, 1, 0, side>>>(flag(d_up_flags, colour, 1), flag(d_down_flags, colour, 0), msgs[colour]);
+  };
+  int rc = TSU_OK;
+  // everything the caller queued on the main stream (e.g. a changed state) precedes the first rows sent
+  cudaEventRecord(ev_join, main);
+  cudaStreamWaitEvent(side, ev_join, 0);
+  send(1);  // colour 0 goes first and reads colour 1
+  bool have_int = false, have_bnd = false;
+  for (int t = 0; t < 2 * n_sweeps && rc == TSU_OK; ++t) {
+    const int colour = t & 1, opp = 1 - colour, k = t & 1;
+    const uint32_t sweep = sweep0 + (uint32_t)(t >> 1);
+    // interior rows on the main stream: they read and overwrite rows next to the boundary rows of the previous half-sweep
+    if (have_bnd) cudaStreamWaitEvent(main, ev_bnd[k ^ 1], 0);
+    rc = launch_half_sweep(d_state, n_replicas, rows, cols, 0, wrap_cols, colour, d_lut, d_lut_index, seed, sweep, replica0,
+                           row0, nullptr, nullptr, main, jit, 1, rows - 1);
+    if (rc != TSU_OK) break;
+    // boundary rows on the side stream: after the previous interior update and the neighbours' rows of the other colour
+    if (have_int) cudaStreamWaitEvent(side, ev_int[k ^ 1], 0);
+    cudaEventRecord(ev_int[k], main);
+    have_int = true;
+    const uint32_t* top = d_up_halo ? halo(d_halo, opp, 0) : nullptr;
+    const uint32_t* bot = d_down_halo ? halo(d_halo, opp, 1) : nullptr;
+    if (top || bot)
+      slab_wait_kernel<<<1, 1, 0, side>>>(top ? flag(d_flags, opp, 0) : nullptr, bot ? flag(d_flags, opp, 1) : nullptr,
+                                          msgs[opp], d_flags + 8);
+    rc = launch_half_sweep(d_state, n_replicas, rows, cols, 0, wrap_cols, colour, d_lut, d_lut_index, seed, sweep, replica0,
+                           row0, top, bot, side, jit, 0, 1);
+    if (rc == TSU_OK)
+      rc = launch_half_sweep(d_state, n_replicas, rows, cols, 0, wrap_cols, colour, d_lut, d_lut_index, seed, sweep, replica0,
+                             row0, top, bot, side, jit, rows - 1, rows);
+    cudaEventRecord(ev_bnd[k], side);
+    have_bnd = true;
+    send(colour);
+  }
+  cudaEventRecord(ev_join, side);
+  cudaStreamWaitEvent(main, ev_join, 0);
+  for (int k = 0; k < 2; ++k) {
+    cudaEventDestroy(ev_int[k]);
+    cudaEventDestroy(ev_bnd[k]);
+  }
+  cudaEventDestroy(ev_join);
+  if (rc != TSU_OK) return rc;
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? TSU_OK : (int)e;
 }
 
 int tsu_ising2d_sweeps(uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows, int wrap_cols,

@@ -54,7 +54,8 @@ class SlabShardedIsing2D:
     previous interior update.  Same launches, same Philox coordinates, same bits as the serial order.
     """
 
-    def __init__(self, rows: int, cols: int, engine_factory, periodic: bool = True, group=None, overlap=None):
+    def __init__(self, rows: int, cols: int, engine_factory, periodic: bool = True, group=None, overlap=None,
+                 transport: str = "auto"):
         dist = _dist()
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -80,6 +81,23 @@ class SlabShardedIsing2D:
         self._side = None
         if self.overlap and st.is_cuda:
             self._side = torch.cuda.Stream(device=st.device, priority=-1)
+        # transport of the halo rows between ranks: "nccl" = send/recv of torch.distributed on the side stream;
+        # "p2p" = the ranks map each other's halo buffers (CUDA IPC over NVLink) and the whole pipeline of a sweep()
+        # call is issued by ONE C-ABI call (tsu_ising2d_slab_sweeps_p2p): no collective library and no Python in the
+        # per-half-sweep path.  "auto" = p2p on CUDA engines with more than one rank, falling back to nccl if the
+        # buffers cannot be mapped.
+        if transport not in ("auto", "nccl", "p2p"):
+            raise ValueError("transport must be 'auto', 'nccl' or 'p2p'")
+        self._p2p = None
+        if transport != "nccl" and self.overlap and st.is_cuda and self.world > 1 and hasattr(self.engine, "lib"):
+            try:
+                self._p2p = _PeerHalos(self)
+            except Exception:
+                if transport == "p2p":
+                    raise
+                self._p2p = None
+        elif transport == "p2p":
+            raise ValueError("transport='p2p' needs a CUDA engine, more than one rank and at least 4 local rows")
 
     @property
     def halo_top(self):  # halos of the colour exchanged last (kept for callers of exchange())
@@ -142,6 +160,9 @@ class SlabShardedIsing2D:
         self.engine.half_sweep(colour, halo_top=top, halo_bot=bot)
 
     def sweep(self, n_sweeps: int = 1):
+        if self._p2p is not None:
+            self._p2p.sweeps(int(n_sweeps))
+            return self
         if not self.overlap:
             for _ in range(n_sweeps):
                 self.half_sweep(0)
@@ -187,6 +208,17 @@ class SlabShardedIsing2D:
             main.wait_stream(self._side)
         return self
 
+    def transport(self) -> str:
+        return "p2p" if self._p2p is not None else ("nccl" if self.world > 1 else "local")
+
+    def close(self):
+        """release the peer-mapped halo buffers (collective: every rank calls it)"""
+        if self._p2p is not None:
+            if self._p2p.status():
+                raise RuntimeError("a neighbour's halo rows did not arrive in time during a slab sweep")
+            self._p2p.close()
+            self._p2p = None
+
     # -- observables -------------------------------------------------------------------------------
     def observables(self):
         """global (# up spins, # anti-aligned bonds) per replica, summed over the slabs"""
@@ -201,6 +233,111 @@ class SlabShardedIsing2D:
         if self.world > 1:
             _dist().all_reduce(obs, group=self.group)
         return obs
+
+
+class _PeerHalos:
+    """halo buffers of a row slab that the ring neighbours map through CUDA IPC, and the one-call sweep pipeline on
+    top of them (include/tsu_b200.h: tsu_ising2d_slab_sweeps_p2p)"""
+
+    FLAG_WORDS = 16
+
+    def __init__(self, drv: "SlabShardedIsing2D"):
+        import ctypes
+
+        import torch
+
+        from . import _lib
+
+        dist = _dist()
+        self.drv = drv
+        eng = drv.engine
+        self.lib = _lib.load()
+        self.device = eng.state.device
+        self.halo_words = 4 * drv.n_replicas * drv.wpr
+        nbytes = 4 * (self.halo_words + self.FLAG_WORDS)
+        with torch.cuda.device(self.device):
+            base = ctypes.c_void_p()
+            _lib.call("tsu_peer_alloc", ctypes.byref(base), nbytes)
+            self.base = base.value
+            handle = ctypes.create_string_buffer(64)
+            _lib.call("tsu_peer_get_handle", ctypes.c_void_p(self.base), handle)
+        mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=self.device)
+        everyone = [torch.empty_like(mine) for _ in range(drv.world)]
+        dist.all_gather(everyone, mine, group=drv.group)
+        self._opened = {}
+
+        def open_rank(r):
+            if r not in self._opened:
+                raw = bytes(everyone[r].cpu().tolist())
+                p = ctypes.c_void_p()
+                with torch.cuda.device(self.device):
+                    _lib.call("tsu_peer_open_handle", ctypes.create_string_buffer(raw, 64), ctypes.byref(p))
+                self._opened[r] = p.value
+            return self._opened[r]
+
+        self.up = open_rank(drv.up) if drv.has_up else None
+        self.down = open_rank(drv.down) if drv.has_down else None
+        self.msgs = [0, 0]
+        dist.barrier(group=drv.group)  # every rank has mapped its neighbours before the first rows are written
+
+    def _flags(self, base):
+        return None if base is None else base + 4 * self.halo_words
+
+    def sweeps(self, n_sweeps: int):
+        import ctypes
+
+        import torch
+
+        from . import _lib
+
+        drv, eng = self.drv, self.drv.engine
+        vp = lambda x: None if x is None else ctypes.c_void_p(x)
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            _lib.call(
+                "tsu_ising2d_slab_sweeps_p2p", int(getattr(eng, "_jit", 0)) if eng.lut_index is None else 0,
+                _lib.ptr(eng.state), eng.n_replicas, eng.rows, eng.cols, int(eng.wrap_cols), _lib.ptr(eng.lut),
+                _lib.ptr(eng.lut_index), eng.seed, eng.sweep_index & 0xFFFFFFFF, int(n_sweeps), eng.replica0, eng.row0,
+                vp(self.base), vp(self._flags(self.base)), vp(self.up), vp(self._flags(self.up)), vp(self.down),
+                vp(self._flags(self.down)), self.msgs[0] & 0xFFFFFFFF, self.msgs[1] & 0xFFFFFFFF,
+                int(main.cuda_stream), int(drv._side.cuda_stream),
+            )
+        self.msgs[0] += n_sweeps
+        self.msgs[1] += n_sweeps + 1
+        eng.sweep_index += n_sweeps
+
+    def status(self) -> int:
+        """0, or 1 if a neighbour's rows did not arrive in time (synchronises the device)"""
+        import ctypes
+
+        import torch
+
+        from . import _lib
+
+        out = ctypes.c_uint32(0)
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            _lib.call("tsu_peer_read_u32", ctypes.c_void_p(self.base + 4 * (self.halo_words + 8)), ctypes.byref(out))
+        return int(out.value)
+
+    def close(self):
+        import ctypes
+
+        import torch
+
+        from . import _lib
+
+        if self.base is None:
+            return
+        torch.cuda.synchronize(self.device)
+        _dist().barrier(group=self.drv.group)  # nobody writes into a buffer that is about to go away
+        with torch.cuda.device(self.device):
+            for p in self._opened.values():
+                _lib.call("tsu_peer_close_handle", ctypes.c_void_p(p))
+            _dist().barrier(group=self.drv.group)
+            _lib.call("tsu_peer_free", ctypes.c_void_p(self.base))
+        self.base = None
+        self._opened = {}
 
 
 class LatticeTempering:
