@@ -238,6 +238,22 @@ int tsu_dense_gibbs_tc_run(const void* d_J_bf16, const float* d_bias, uint8_t* d
 int tsu_dense_tc_debug_fields(const void* d_J_bf16, const uint8_t* d_state, int n_chains, int N,
                               float* d_fields, uintptr_t stream);
 
+/* Chromatic Gibbs sweeps for SPARSE couplings (csrc/sparse_gibbs.cu): IsingChain (tsu/models/ising.py:265-304),
+ * irregular graphs, MAX-CUT instances.  J in CSR (row i = couplings into site i, ascending columns, self term
+ * allowed), sites grouped into colour classes such that no two coupled sites share one (d_colour_sites, offsets in
+ * d_colour_ptr).  A sweep visits the classes in order; the sites of a class are updated concurrently, which equals
+ * the reference's sequential sweep (tsu/gibbs.py:153-160) in that visiting order - update_order="random" with the
+ * class order as the permutation.  One CTA per chain, bits in shared memory (N <= 204800), float64 fields;
+ * schedule, outputs, per-chain / per-sweep temperatures and best-state tracking as in tsu_dense_gibbs_run, and the
+ * same Philox uniforms per (site, chain, sweep).  d_uniforms (parity mode): [sweep][chain][N] in visiting order. */
+int tsu_sparse_gibbs_run(const int32_t* d_rowptr, const int32_t* d_col, const double* d_val,
+                         const double* d_bias, const int32_t* d_colour_ptr, const int32_t* d_colour_sites,
+                         int n_colours, uint8_t* d_state, int n_chains, int N, double T,
+                         const double* d_T_chain, const double* d_T_sweep, int n_burnin, int n_samples,
+                         int sweeps_per_sample, const double* d_uniforms, uint8_t* d_samples, double* d_energy,
+                         int track_best, uint8_t* d_best_state, double* d_best_energy, uint64_t seed,
+                         uint32_t sweep0, uint32_t chain0, uintptr_t stream);
+
 /* Replica-exchange pass (tsu/gibbs.py:308-323): for each ladder, pairs i = 0..R-2 in order;
  * delta = (1/T_i - 1/T_{i+1}) (E_{i+1} - E_i); accept if delta >= 0 or u < exp(delta) (u drawn
  * only when delta < 0).  Configurations stay in place; d_slot_replica[ladder][i] (the replica

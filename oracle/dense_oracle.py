@@ -160,3 +160,21 @@ def tc_sweep_disagreements(start, after, coupling, bias, T, uniforms):
             out.append((i, abs(float(uniforms[i]) - p)))
         cur[i] = after[i]
     return out
+
+
+def greedy_colour_order(coupling):
+    """visiting order of the chromatic sparse sampler: greedy colouring (sites in index order take the smallest colour
+    no coupled, already coloured site has; coupling in either direction counts), then colour 0's sites in ascending
+    index, colour 1's, ...  A valid permutation for the reference's update_order="random" (gibbs.py:155-157)."""
+    J = np.asarray(coupling)
+    N = J.shape[0]
+    adj = (J != 0) | (J.T != 0)
+    np.fill_diagonal(adj, False)
+    colour = -np.ones(N, dtype=np.int64)
+    for i in range(N):
+        used = set(colour[np.flatnonzero(adj[i])].tolist())
+        c = 0
+        while c in used:
+            c += 1
+        colour[i] = c
+    return np.argsort(colour, kind="stable"), colour

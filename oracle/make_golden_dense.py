@@ -126,6 +126,44 @@ def tempering_case(name, n, temps, burnin, n_sweeps, n_samples, swap_interval, s
                         energies=np.array(info["energies"]), final_states=np.array(info["final_states"]))
 
 
+def chromatic_case(name, J, b, T, n_sweeps, seed):
+    """sparse couplings: the reference's sweep with update_order="random" and the permutation fixed to the greedy
+    colour-class order - what csrc/sparse_gibbs.cu computes with the classes updated concurrently"""
+    from unittest import mock
+
+    from . import dense_oracle as D
+
+    gibbs, _, _ = load_reference()
+    rng = np.random.default_rng(seed)
+    n = J.shape[0]
+    order, colour = D.greedy_colour_order(J)
+    s0 = rng.integers(0, 2, n)
+    U = rng.random((n_sweeps, n))   # U[t, k] is consumed by the k-th visited site of sweep t
+    smp = gibbs.GibbsSampler(gibbs.GibbsConfig(temperature=T, update_order="random"))
+    with injected_numpy_random(uniforms=U.ravel()), mock.patch("numpy.random.permutation", lambda k: order.copy()):
+        out = smp.gibbs_sweep(s0.copy(), J, b, n_sweeps=n_sweeps)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, f"sparse_sweep_{name}.npz"), J=J, b=b, T=T, s0=s0, uniforms=U,
+                        order=order, colour=colour, out=out, energy=smp.compute_energy(out, J, b))
+
+
+def chromatic_cases():
+    _, _, ising = load_reference()
+    # the bit model of the reference's IsingChain (ising.py:265-304, 127-138) with the physical bias
+    ch = ising.IsingChain(41, J=0.8, config=ising.IsingConfig(temperature=1.2, external_field=0.3))
+    chromatic_case("chain41", 4 * ch.J, 2 * ch.h - 2 * ch.J.sum(1), 1.2, 4, 31)
+    # irregular sparse graph with a few self-couplings and integer weights
+    rng = np.random.default_rng(32)
+    n = 60
+    J = np.zeros((n, n))
+    for _ in range(130):
+        i, j = rng.integers(0, n, 2)
+        if i != j:
+            J[i, j] = J[j, i] = float(rng.integers(-2, 3))
+    for i in rng.choice(n, 5, replace=False):
+        J[i, i] = float(rng.integers(1, 3))
+    chromatic_case("graph60", J, rng.normal(size=n) * 0.5, 0.9, 3, 33)
+
+
 def main():
     sweep_case("n12_seq", 12, 1.3, 5, "sequential", 21)
     sweep_case("n33_rand", 33, 0.8, 4, "random", 22)
@@ -135,6 +173,7 @@ def main():
     annealing_case("n14_exp", 14, 25, "exponential", 26)
     annealing_case("n9_lin", 9, 12, "linear", 27)
     tempering_case("n10_r4", 10, [0.5, 1.0, 2.0, 4.0], 2, 2, 8, 2, 28)
+    chromatic_cases()
     print("dense goldens written")
 
 

@@ -136,3 +136,89 @@ def test_p_bit_categorical_and_neuron():
     assert r["passes_test"] and r["n_samples"] == 5000
     g = ThermalSamplingUnit(seed=6).sample_gaussian(mu=0, sigma=1, n_samples=2000)
     assert validate_distribution(g, "gaussian", {"mu": 0, "sigma": 1}, alpha=0.001)["passes_ks_test"]
+
+
+def _oracle_vs_kernel(energy, energy_fn, x_init, n_samples, cfg_kw, atol, dtype="float64", seed=3):
+    """injected normals through the fused kernel and through the oracle's restatement of core.py:100-162 (which
+    differentiates numerically, eps = 1e-5, like the reference)"""
+    from oracle import langevin_oracle as LO
+    from tsu_emulator_b200 import ThermalSamplingUnit, TSUConfig
+
+    cfg = TSUConfig(**cfg_kw)
+    x_init = np.atleast_1d(np.asarray(x_init, dtype=np.float64))
+    rng = np.random.default_rng(seed)
+    normals = rng.normal(size=(n_samples, 1 + cfg.n_burnin + cfg.n_steps, x_init.size))
+    got, traj = ThermalSamplingUnit(cfg, dtype=dtype, seed=1).sample_from_energy(
+        energy, x_init, n_samples, return_trajectory=True, _normals=normals)
+    want, wtraj = LO.sample_from_energy(energy_fn, x_init, n_samples, normals, temperature=cfg.temperature, dt=cfg.dt,
+                                        friction=cfg.friction, n_burnin=cfg.n_burnin, n_steps=cfg.n_steps,
+                                        return_trajectory=True)
+    assert np.allclose(got, want, rtol=0, atol=atol), np.abs(got - want).max()
+    assert np.allclose(np.array(traj), np.array(wtraj), rtol=0, atol=atol)
+
+
+def test_double_well_energy_matches_reference_loop():
+    """DoubleWellEnergy E = sum a (x^2 - b)^2 (bimodal landscape, wells at +-sqrt(b)): analytic gradient in
+    the kernel against the numerically differentiated reference loop, float64 1e-7 / float32 5e-4 (tolerances: the
+    central difference of a quartic has a relative error ~eps^2 x''' ~ 1e-9 per step, accumulated over 60 steps)"""
+    from tsu_emulator_b200 import DoubleWellEnergy
+
+    a, b = 0.7, 1.3
+    fn = lambda x: float(np.sum(a * (np.asarray(x) ** 2 - b) ** 2))
+    e = DoubleWellEnergy(a, b)
+    assert e(np.array([0.3, -1.2])) == pytest.approx(fn(np.array([0.3, -1.2])), abs=1e-12)
+    kw = dict(temperature=0.8, dt=0.02, friction=1.5, n_burnin=20, n_steps=40)
+    _oracle_vs_kernel(e, fn, [0.2, -0.4, 1.1], 6, kw, 1e-7)
+    _oracle_vs_kernel(e, fn, [0.2, -0.4, 1.1], 6, kw, 5e-4, dtype="float32")
+    # by name (a = b = 1), and statistically: the two wells at +-1 are both populated
+    from tsu_emulator_b200 import ThermalSamplingUnit, TSUConfig
+    s = ThermalSamplingUnit(TSUConfig(temperature=0.5, n_burnin=200, n_steps=800), seed=2).sample_from_energy(
+        "double_well", np.zeros(1), 4000)
+    assert 0.35 < (s > 0).mean() < 0.65 and abs(np.abs(s).mean() - 1.0) < 0.15
+
+
+def test_mean_reduced_gaussian_energy_matches_reference_loop():
+    """GaussianEnergy(reduce='mean') = the energy of the reference's GaussianSampler (api.py:124-126: the MEAN over the
+    coordinates, so each coordinate feels 1/dim of the force)"""
+    from tsu_emulator_b200 import GaussianEnergy
+
+    mu, sigma = np.array([1.0, -2.0, 0.5]), np.array([0.5, 2.0, 1.0])
+    fn = lambda x: float(np.mean(0.5 * ((np.asarray(x) - mu) / sigma) ** 2))
+    e = GaussianEnergy(mu, sigma, reduce="mean")
+    kw = dict(temperature=1.0, dt=0.05, friction=1.0, n_burnin=10, n_steps=50)
+    _oracle_vs_kernel(e, fn, [0.0, 0.0, 0.0], 5, kw, 1e-8)
+    _oracle_vs_kernel(e, fn, [0.0, 0.0, 0.0], 5, kw, 2e-4, dtype="float32")
+
+
+def test_api_samplers_on_the_b200_backend():
+    """tsu/api.py:38-218 facade: Backend.B200 (and EMULATOR as its alias), GaussianSampler / MultimodalSampler /
+    BayesianSampler.sample, SamplingResult metadata, the functional helpers; unknown backends raise like the reference"""
+    from tsu_emulator_b200 import SamplingError, TSUConfig
+    from tsu_emulator_b200.api import (Backend, BayesianSampler, GaussianSampler, MultimodalSampler, SamplingResult,
+                                       sample_gaussian, sample_multimodal)
+
+    cfg = TSUConfig(n_burnin=200, n_steps=800)
+    g = GaussianSampler(mu=3.0, sigma=0.5, config=cfg, seed=1)
+    assert g.backend == Backend.B200
+    s = g.sample(4000)
+    assert s.shape == (4000, 1) and abs(s.mean() - 3.0) < 0.05 and abs(s.std() - 0.5) < 0.05
+    r = GaussianSampler(mu=0.0, sigma=1.0, backend=Backend.EMULATOR, config=cfg, seed=2).sample(100, return_metadata=True)
+    assert isinstance(r, SamplingResult) and r.samples.shape == (100, 1) and r.time_elapsed > 0 and r.backend_used == "b200"
+    with pytest.raises(NotImplementedError):
+        GaussianSampler(backend=Backend.CLOUD).sample(10)
+    m = MultimodalSampler(centers=[[-3.0, 0.0], [3.0, 0.0]], weights=[1.0, 1.0], config=cfg, seed=3)
+    x = m.sample(4000)
+    assert x.shape == (4000, 2)
+    near = np.minimum(np.abs(x[:, 0] + 3.0), np.abs(x[:, 0] - 3.0))
+    assert near.mean() < 1.2 and 0.2 < (x[:, 0] > 0).mean() < 0.8
+    assert sample_gaussian(1.0, 2.0, n=50).shape == (50, 1) and sample_multimodal([[0.0], [4.0]], [1, 1], n=20).shape == (20, 1)
+    # linear-Gaussian posterior (the reference's docstring example) is a quadratic form: recognised and exact
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(30, 2)); y = X @ np.array([1.5, -0.5]) + 0.1 * rng.normal(size=30)
+    b = BayesianSampler(lambda th, X_, y_: -0.5 * np.sum((y_ - X_ @ th) ** 2), lambda th: -0.5 * np.sum(th ** 2), X, y,
+                        dim=2, config=TSUConfig(dt=0.005, n_burnin=400, n_steps=1200), seed=4)
+    post = b.sample(3000)
+    cov = np.linalg.inv(X.T @ X + np.eye(2)); mean = cov @ X.T @ y
+    assert np.abs(post.mean(0) - mean).max() < 0.05
+    with pytest.raises(SamplingError):   # a non-quadratic posterior cannot run on the device
+        BayesianSampler(lambda th: -np.sum(np.abs(th) ** 3), lambda th: 0.0, dim=2).sample(4)

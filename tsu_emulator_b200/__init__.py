@@ -33,3 +33,11 @@ from .models import (  # noqa: F401
     IsingModel2D,
     demonstrate_phase_transition,
 )
+from .api import (  # noqa: F401,E402
+    Backend,
+    BayesianSampler,
+    GaussianSampler,
+    MultimodalSampler,
+    Sampler,
+    SamplingResult,
+)

@@ -231,8 +231,10 @@ def recognise_quadratic(energy_fn: Callable, dim: int, x0: np.ndarray, rtol: flo
 class ThermalSamplingUnit:
     """tsu/core.py:54-267 with the Langevin loop fused into one CUDA kernel (one thread per chain)."""
 
-    def __init__(self, config: Optional[TSUConfig] = None, *, seed: Optional[int] = None, dtype: str = "float32",
+    def __init__(self, config: Optional[TSUConfig] = None, *, seed: Optional[int] = None, dtype: str = "float64",
                  device=None):
+        """dtype: arithmetic of the chains.  "float64" (default) is the reference's (numpy float64, core.py:64-80);
+        "float32" is the opt-in fast path (MUFU Box-Muller, ~4.6x faster, trajectories within 2e-4 of float64)."""
         self.config = config or TSUConfig()
         self.sample_count = 0
         if dtype not in ("float32", "float64"):

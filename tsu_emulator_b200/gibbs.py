@@ -240,9 +240,40 @@ class GibbsSampler:
             o = torch.from_numpy(np.ascontiguousarray(np.asarray(orders, dtype=np.int32))).to(prob.device)
         return u, o
 
+    def _sparse(self, coupling, bias):
+        """couplings in CSR form + colour classes on the device (csrc/sparse_gibbs.cu); float64 fields"""
+        from .sparse import SparseProblem
+
+        if self.precision != "float64":
+            raise ValueError("chromatic=True (sparse couplings) computes float64 fields: use a 'float64' sampler")
+        return SparseProblem(coupling, bias, self._dev())
+
+    def _sparse_run(self, prob, state, uniforms=None, **kw):
+        from . import sparse
+
+        torch = _lib.require_cuda()
+        u = None
+        if uniforms is not None:  # parity mode: [sweeps, N] or [sweeps, chains, N] float64 in VISITING order
+            a = np.asarray(uniforms, dtype=np.float64)
+            if a.ndim == 2:
+                a = a[:, None, :]
+            u = torch.from_numpy(np.ascontiguousarray(a)).to(prob.device)
+        total = kw["n_burnin"] + kw["n_samples"] * kw["sweeps_per_sample"]
+        out = sparse.run(prob, state, T=float(self.config.temperature), seed=self._seed, sweep0=self._sweep_counter,
+                         chain0=self._chain_counter, uniforms=u, **kw)
+        self._sweep_counter += total
+        return out
+
     def gibbs_sweep(self, state: np.ndarray, coupling: np.ndarray, bias: Optional[np.ndarray] = None,
-                    n_sweeps: int = 1, *, _uniforms=None, _orders=None) -> np.ndarray:
-        """tsu/gibbs.py:128-162: n_sweeps sweeps over all bits; the input is not modified (gibbs.py:150)"""
+                    n_sweeps: int = 1, *, chromatic: bool = False, _uniforms=None, _orders=None) -> np.ndarray:
+        """tsu/gibbs.py:128-162: n_sweeps sweeps over all bits; the input is not modified (gibbs.py:150).
+        chromatic=True: sparse couplings, sites visited colour class by colour class (csrc/sparse_gibbs.cu)"""
+        if chromatic:
+            prob = self._sparse(coupling, bias)
+            st = self._initial_states(prob, 1, np.asarray(state))
+            self._sparse_run(prob, st, uniforms=_uniforms, n_burnin=int(n_sweeps), n_samples=0, sweeps_per_sample=0)
+            a = np.asarray(state)
+            return st[0].cpu().numpy().astype(a.dtype if a.dtype.kind in "iu" else np.int64)
         prob = _DenseProblem(coupling, bias, self.precision, self._dev())
         st = self._initial_states(prob, 1, np.asarray(state))
         u, o = self._inject(prob, _uniforms, _orders)
@@ -252,13 +283,28 @@ class GibbsSampler:
 
     def sample_boltzmann(self, coupling: np.ndarray, bias: Optional[np.ndarray] = None, n_samples: int = 1000,
                          burnin: Optional[int] = None, initial_state: Optional[np.ndarray] = None, *,
-                         n_chains: int = 1, as_tensor: bool = False, _uniforms=None, _orders=None):
+                         n_chains: int = 1, as_tensor: bool = False, chromatic: bool = False, _uniforms=None,
+                         _orders=None):
         """tsu/gibbs.py:164-213: burn-in, then n_samples x config.n_sweeps sweeps; one launch.
 
         n_chains == 1 (default): int array (n_samples, n_bits) like the reference.
         n_chains > 1: (n_chains, n_samples, n_bits) - independent chains run concurrently.
+        chromatic=True: sparse couplings (dense array, scipy.sparse matrix or CSR tuple) on the chromatic CSR kernel;
+        a sweep visits the sites colour class by colour class instead of in index order.
         """
         burnin = burnin if burnin is not None else self.config.n_burnin
+        if chromatic:
+            prob = self._sparse(coupling, bias)
+            st = self._initial_states(prob, int(n_chains), initial_state)
+            samples, _, _, _ = self._sparse_run(prob, st, uniforms=_uniforms, n_burnin=int(burnin),
+                                                n_samples=int(n_samples), sweeps_per_sample=self.config.n_sweeps,
+                                                want_samples=True)
+            self._chain_counter += int(n_chains)
+            self.sample_count += int(n_samples)
+            if as_tensor:
+                return samples if n_chains > 1 else samples[:, 0]
+            out = samples.cpu().numpy().astype(int)
+            return out[:, 0, :] if n_chains == 1 else np.ascontiguousarray(out.transpose(1, 0, 2))
         if self.precision == "bf16":
             if _uniforms is not None or _orders is not None:
                 raise ValueError("injected draws are a float64 / float32 parity mode; precision='bf16' draws Philox")
@@ -425,14 +471,15 @@ class GibbsSampler:
 
     def simulated_annealing(self, coupling: np.ndarray, bias: Optional[np.ndarray] = None, T_initial: float = 10.0,
                             T_final: float = 0.1, n_steps: int = 1000, cooling_schedule: str = "exponential", *,
-                            n_chains: int = 1, _uniforms=None, _initial_state=None) -> Tuple[np.ndarray, float]:
+                            n_chains: int = 1, chromatic: bool = False, _uniforms=None,
+                            _initial_state=None) -> Tuple[np.ndarray, float]:
         """tsu/gibbs.py:340-393: one sweep per step at the scheduled temperature, lowest energy tracked.
 
         The whole anneal is one kernel launch (per-sweep temperature array, on-device best tracking).
         With n_chains > 1 that many independent anneals run concurrently and the best is returned.
         """
         torch = _lib.require_cuda()
-        prob = _DenseProblem(coupling, bias, self.precision, self._dev())
+        prob = self._sparse(coupling, bias) if chromatic else _DenseProblem(coupling, bias, self.precision, self._dev())
         steps = np.arange(n_steps, dtype=np.float64)
         if cooling_schedule == "exponential":
             Ts = T_initial * (T_final / T_initial) ** (steps / n_steps)
@@ -442,16 +489,31 @@ class GibbsSampler:
         if n_steps > 0:
             T_sweep = torch.from_numpy(Ts).to(prob.device)
             self.config.temperature = float(Ts[-1])  # the reference leaves the last T in the config (gibbs.py:382)
-            u, _ = self._inject(prob, _uniforms, None)
-            _, _, best_state, best_energy = self._run(prob, st, n_burnin=int(n_steps), n_samples=0,
-                                                      sweeps_per_sample=0, T_sweep=T_sweep, track_best=True,
-                                                      uniforms=u)
+            if chromatic:
+                _, _, best_state, best_energy = self._sparse_run(prob, st, uniforms=_uniforms, n_burnin=int(n_steps),
+                                                                 n_samples=0, sweeps_per_sample=0, T_sweep=T_sweep,
+                                                                 track_best=True)
+            else:
+                u, _ = self._inject(prob, _uniforms, None)
+                _, _, best_state, best_energy = self._run(prob, st, n_burnin=int(n_steps), n_samples=0,
+                                                          sweeps_per_sample=0, T_sweep=T_sweep, track_best=True,
+                                                          uniforms=u)
             be = best_energy.cpu().numpy()
             k = int(np.argmin(be))
             state = best_state[k].cpu().numpy().astype(int)
         else:
             state = st[0].cpu().numpy().astype(int)
         self._chain_counter += int(n_chains)
+        if chromatic:
+            from .sparse import to_csr
+
+            rowptr, col, val, _ = to_csr(coupling)
+            sb = state.astype(np.float64)
+            row = np.repeat(np.arange(len(sb)), np.diff(rowptr))
+            e = -0.5 * float(np.sum(val * sb[row] * sb[col]))
+            if bias is not None:
+                e -= float(np.dot(np.asarray(bias, dtype=np.float64), sb))
+            return state, e
         J = np.asarray(coupling, dtype=np.float64)
         return state, self.compute_energy(state, J, None if bias is None else np.asarray(bias, dtype=np.float64))
 

@@ -57,7 +57,8 @@ class IsingModel:
             config = IsingConfig(temperature=temperature) if temperature is not None else IsingConfig()
         self.config = config
         self.compat_reference_bias = bool(compat_reference_bias)
-        self._J = np.zeros((self.n_spins, self.n_spins))
+        # subclasses that know their wiring (IsingChain, IsingGrid) build the dense matrix only on demand
+        self._J = None if getattr(self, "_lazy", False) else np.zeros((self.n_spins, self.n_spins))
         self.h = np.ones(self.n_spins) * self.config.external_field
         if J is not None:
             Jm = np.asarray(J, dtype=np.float64)
@@ -121,12 +122,19 @@ class IsingModel:
         self.sampler.config.n_burnin = self.config.n_burnin
         self.sampler.config.n_sweeps = self.config.n_sweeps
 
+    def _chromatic(self) -> bool:
+        """mostly empty coupling matrices run on the chromatic CSR kernel (a sweep costs nnz, not N^2)"""
+        from ..sparse import is_sparse_enough
+
+        return is_sparse_enough(self.J)
+
     def sample(self, n_samples: int = 1000, initial_state: Optional[np.ndarray] = None) -> np.ndarray:
         """ising.py:150-181: (n_samples, n_spins) configurations in {-1,+1} from the Boltzmann distribution"""
         self._sync_sampler_config()
         initial_bits = self._spins_to_bits(initial_state) if initial_state is not None else None
         bit_samples = self.sampler.sample_boltzmann(
-            self._get_bit_coupling(), bias=self._get_bit_bias(), n_samples=n_samples, initial_state=initial_bits
+            self._get_bit_coupling(), bias=self._get_bit_bias(), n_samples=n_samples, initial_state=initial_bits,
+            chromatic=self._chromatic(),
         )
         return self._bits_to_spins(bit_samples)
 
@@ -155,19 +163,92 @@ class IsingModel:
         self._sync_sampler_config()
         best_bits, _ = self.sampler.simulated_annealing(
             self._get_bit_coupling(), bias=self._get_bit_bias(), T_initial=10.0 * self.config.temperature,
-            T_final=0.01 * self.config.temperature, n_steps=n_steps,
+            T_final=0.01 * self.config.temperature, n_steps=n_steps, chromatic=self._chromatic(),
         )
         ground_state = self._bits_to_spins(best_bits)
         return ground_state, self.energy(ground_state)
 
 
 class IsingChain(IsingModel):
-    """1-D nearest-neighbour chain (ising.py:265-304)"""
+    """1-D nearest-neighbour chain (ising.py:265-304).  The reference fills a dense n x n matrix with the n - 1 bonds;
+    here the matrix exists only if somebody reads or edits `.J` - sampling, annealing and energies use the two
+    off-diagonals directly (chromatic CSR kernel: the chain is two-colourable), so n_spins can be 10^5."""
 
     def __init__(self, n_spins: int, J: float = 1.0, config: Optional[IsingConfig] = None, **kw):
+        self._chain_J = float(J)
+        self._lazy = True
         super().__init__(n_spins, config, **kw)
-        for i in range(n_spins - 1):
-            self.set_coupling(i, i + 1, J)
+
+    @property
+    def J(self) -> np.ndarray:
+        if self._J is None:
+            n = self.n_spins
+            Jm = np.zeros((n, n))
+            i = np.arange(n - 1)
+            Jm[i, i + 1] = self._chain_J
+            Jm[i + 1, i] = self._chain_J
+            self._J = Jm
+        return self._J
+
+    @J.setter
+    def J(self, value):
+        self._J = np.asarray(value, dtype=np.float64)
+
+    def _bit_csr(self):
+        """(CSR of J_bit = 4 J, h_bit) of the untouched chain (ising.py:127-148 without the dense matrix)"""
+        n, Jc = self.n_spins, self._chain_J
+        deg = np.full(n, 2.0)
+        if n > 0:
+            deg[0] -= 1
+            deg[-1] -= 1
+        if n == 1:
+            deg[:] = 0
+        rowsum = Jc * deg
+        rowptr = np.concatenate([[0], np.cumsum(deg.astype(np.int64))]).astype(np.int32)
+        col = np.empty(int(rowptr[-1]), dtype=np.int32)
+        k = 0
+        for i in range(n):   # ascending columns: i - 1 then i + 1
+            if i > 0:
+                col[k] = i - 1
+                k += 1
+            if i < n - 1:
+                col[k] = i + 1
+                k += 1
+        val = np.full(col.size, 4.0 * Jc)
+        bias = (-2 * self.h + 2 * rowsum) if self.compat_reference_bias else (2 * self.h - 2 * rowsum)
+        return (rowptr, col, val, n), bias
+
+    def sample(self, n_samples: int = 1000, initial_state: Optional[np.ndarray] = None) -> np.ndarray:
+        if self._J is not None:   # somebody edited the couplings: general path
+            return super().sample(n_samples, initial_state)
+        self._sync_sampler_config()
+        csr, bias = self._bit_csr()
+        initial_bits = self._spins_to_bits(initial_state) if initial_state is not None else None
+        bits = self.sampler.sample_boltzmann(csr, bias=bias, n_samples=n_samples, initial_state=initial_bits, chromatic=True)
+        return self._bits_to_spins(bits)
+
+    def find_ground_state(self, n_steps: int = 1000) -> Tuple[np.ndarray, float]:
+        if self._J is not None:
+            return super().find_ground_state(n_steps)
+        self._sync_sampler_config()
+        csr, bias = self._bit_csr()
+        best_bits, _ = self.sampler.simulated_annealing(csr, bias=bias, T_initial=10.0 * self.config.temperature,
+                                                        T_final=0.01 * self.config.temperature, n_steps=n_steps,
+                                                        chromatic=True)
+        gs = self._bits_to_spins(best_bits)
+        return gs, self.energy(gs)
+
+    def energy(self, state: np.ndarray) -> float:
+        if self._J is not None:
+            return super().energy(state)
+        s = np.asarray(state, dtype=np.float64)
+        return float(-self._chain_J * np.dot(s[:-1], s[1:]) - self.h.dot(s))
+
+    def _energies(self, samples: np.ndarray) -> np.ndarray:
+        if self._J is not None:
+            return super()._energies(samples)
+        s = np.asarray(samples, dtype=np.float64)
+        return -self._chain_J * np.sum(s[:, :-1] * s[:, 1:], axis=1) - s @ self.h
 
 
 def _grid_coupling_matrix(rows: int, cols: int, J: float, periodic: bool) -> np.ndarray:
