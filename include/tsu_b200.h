@@ -293,6 +293,21 @@ int tsu_langevin_run(void* d_x, int dtype, int64_t n_chains, int dim, int energy
                      int first_chain_exact, double T, double dt, double gamma, int n_burnin, int n_steps, uint64_t seed,
                      uint64_t chain0, const void* d_normals, void* d_traj, uintptr_t stream);
 
+/* Langevin chains for an energy that is not built in: the caller supplies the GRADIENT as CUDA source,
+ *     template <typename real> __device__ __forceinline__ void tsu_user_grad(const real* x, real* g) { ... }
+ * (tsu_emulator_b200/trace.py writes it from a traced and analytically differentiated Python callable - the
+ * reference differentiates such callables numerically on the host, tsu/core.py:82-98), and NVRTC compiles it into
+ * the same chain loop as the built-in energies (csrc/langevin_body.cuh) for one (dtype, dim).  src_dir = directory
+ * of langevin_body.cuh and philox.cuh.  Returns a handle >= 1, or 0 when NVRTC / the driver API is unavailable or
+ * the source does not compile (log_buf gets the reason).  tsu_langevin_run_jit takes the arguments of
+ * tsu_langevin_run minus the energy description. */
+int tsu_langevin_jit_prepare(const char* grad_source, int dtype, int dim, const char* src_dir,
+                             char* log_buf, int log_len);
+int tsu_langevin_run_jit(int handle, void* d_x, int64_t n_chains, const void* d_x_init, double jitter,
+                         int first_chain_exact, double T, double dt, double gamma, int n_burnin,
+                         int n_steps, uint64_t seed, uint64_t chain0, const void* d_normals,
+                         void* d_traj, uintptr_t stream);
+
 #ifdef __cplusplus
 }
 #endif

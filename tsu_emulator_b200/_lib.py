@@ -115,6 +115,12 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_uint64, c_uint32, c_void_p, c_void_p, c_int,
          c_uintptr],
     ),
+    "tsu_langevin_jit_prepare": (c_int, [c_char_p, c_int, c_int, c_char_p, c_char_p, c_int]),
+    "tsu_langevin_run_jit": (
+        c_int,
+        [c_int, c_void_p, c_int64, c_void_p, c_double, c_int, c_double, c_double, c_double, c_int, c_int, c_uint64,
+         c_uint64, c_void_p, c_void_p, c_uintptr],
+    ),
     "tsu_langevin_run": (
         c_int,
         [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_double, c_int, c_double, c_double,

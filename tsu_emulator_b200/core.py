@@ -4,12 +4,16 @@ the exception types) with the sampling loop on the B200 (csrc/langevin.cu, tsu_l
 
 The reference differentiates an arbitrary Python `energy_fn` numerically (core.py:82-98) - 2*dim
 Python callbacks per step.  A Python callable cannot run on the GPU and there is no CPU fallback, so
-`sample_from_energy` accepts
-  * built-in energy objects (QuadraticEnergy, GaussianEnergy, MixtureEnergy, DoubleWellEnergy), or
-  * a Python callable that is *recognised* as an exact quadratic form: it is probed at 1 + 2d + d(d-1)/2
-    points, the fitted quadratic is verified on random points, and the chain then runs on the fused
-    kernel with the analytic gradient.  README's `lambda x: (x**2).sum()` and core.py's Gaussian
-    energy (core.py:227-230) are of this kind.  Anything else raises SamplingError.
+`sample_from_energy` resolves the energy in this order:
+  1. built-in energy objects (QuadraticEnergy, GaussianEnergy, MixtureEnergy, DoubleWellEnergy) and their names;
+  2. a Python callable that is *recognised* as an exact quadratic form: it is probed at 1 + 2d + d(d-1)/2
+     points, the fitted quadratic is verified on random points, and the chain runs on the prebuilt kernel with the
+     analytic gradient (README's `lambda x: (x**2).sum()`, core.py's Gaussian energy, core.py:227-230);
+  3. any other callable is TRACED (tsu_emulator_b200/trace.py): called once on symbolic inputs, differentiated
+     analytically, and its gradient compiled by NVRTC into the same chain loop (1-2 s per new function, cached).
+     Double wells, mixtures written as Python loops, Rosenbrock-like landscapes, posteriors over data run this way;
+  4. what cannot be traced - branches on the value of x, float(...) of an intermediate, calls into compiled code -
+     raises SamplingError with the reason.
 """
 
 from dataclasses import dataclass
@@ -227,6 +231,28 @@ def recognise_quadratic(energy_fn: Callable, dim: int, x0: np.ndarray, rtol: flo
         return None
 
 
+class TracedEnergy(BuiltinEnergy):
+    """a Python callable turned into CUDA source for its analytic gradient (trace.py); compiled at first use"""
+
+    kind = 100
+
+    def __init__(self, energy_fn: Callable, dim: int, x0: np.ndarray):
+        from .trace import trace_energy
+
+        rng = np.random.default_rng(20240229)
+        probes = np.asarray(x0, dtype=np.float64)[None, :] + rng.normal(size=(4, dim))
+        tr, _, grads = trace_energy(energy_fn, dim, probes)
+        self.fn, self.dim = energy_fn, dim
+        self.source = tr.cuda_source(grads)
+        self.n_nodes = self.source.count("\n")
+
+    def params(self, dim):
+        return np.zeros(1)
+
+    def __call__(self, x):
+        return float(self.fn(np.atleast_1d(np.asarray(x, dtype=np.float64))))
+
+
 # ----------------------------------------------------------------------------- the sampler
 class ThermalSamplingUnit:
     """tsu/core.py:54-267 with the Langevin loop fused into one CUDA kernel (one thread per chain)."""
@@ -277,11 +303,16 @@ class ThermalSamplingUnit:
             q = recognise_quadratic(energy_fn, x_init.size, x_init)
             if q is not None:
                 return q.as_diagonal() or q
-        raise SamplingError(
-            "energy function is neither a built-in energy (QuadraticEnergy, GaussianEnergy, MixtureEnergy, "
-            "DoubleWellEnergy) nor recognisable as a quadratic form; arbitrary Python callables cannot run on the "
-            "GPU and this engine has no CPU fallback"
-        )
+            from .trace import TraceError
+
+            try:
+                return TracedEnergy(energy_fn, x_init.size, x_init)
+            except TraceError as exc:
+                raise SamplingError(
+                    "energy function is neither a built-in energy (QuadraticEnergy, GaussianEnergy, MixtureEnergy, "
+                    "DoubleWellEnergy), nor a quadratic form, nor traceable into CUDA: " + str(exc) +
+                    ".  Arbitrary Python control flow cannot run on the GPU and this engine has no CPU fallback")
+        raise SamplingError("energy must be a built-in energy object, its name, or a Python callable")
 
     def _launch(self, energy: BuiltinEnergy, x_init: np.ndarray, n_chains: int, return_trajectory: bool,
                 normals=None, as_tensor: bool = False):
@@ -303,12 +334,28 @@ class ThermalSamplingUnit:
             if tuple(nrm.shape) != (n_chains, 1 + cfg.n_burnin + cfg.n_steps, dim):
                 raise SamplingError("injected normals must have shape (n_chains, 1 + n_burnin + n_steps, dim)")
         with torch.cuda.device(device):
-            _lib.call(
-                "tsu_langevin_run", ptr(x), code, int(n_chains), int(dim), int(energy.kind), ptr(params),
-                int(params.numel()), ptr(x0), 0.1, 1, float(cfg.temperature), float(cfg.dt), float(cfg.friction),
-                int(cfg.n_burnin), int(cfg.n_steps), self._seed, self._chain_counter, ptr(nrm), ptr(traj),
-                _lib.current_stream(),
-            )
+            if isinstance(energy, TracedEnergy):
+                import ctypes
+                import os
+
+                log = ctypes.create_string_buffer(8192)
+                src_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc").encode()
+                handle = int(_lib.load().tsu_langevin_jit_prepare(energy.source.encode(), code, int(dim), src_dir, log, 8192))
+                if handle <= 0:
+                    raise SamplingError("the traced energy could not be compiled for the GPU: " +
+                                        log.value.decode(errors="replace")[:2000])
+                _lib.call(
+                    "tsu_langevin_run_jit", handle, ptr(x), int(n_chains), ptr(x0), 0.1, 1, float(cfg.temperature),
+                    float(cfg.dt), float(cfg.friction), int(cfg.n_burnin), int(cfg.n_steps), self._seed,
+                    self._chain_counter, ptr(nrm), ptr(traj), _lib.current_stream(),
+                )
+            else:
+                _lib.call(
+                    "tsu_langevin_run", ptr(x), code, int(n_chains), int(dim), int(energy.kind), ptr(params),
+                    int(params.numel()), ptr(x0), 0.1, 1, float(cfg.temperature), float(cfg.dt), float(cfg.friction),
+                    int(cfg.n_burnin), int(cfg.n_steps), self._seed, self._chain_counter, ptr(nrm), ptr(traj),
+                    _lib.current_stream(),
+                )
         if normals is None:
             self._chain_counter += n_chains
         self.sample_count += n_chains

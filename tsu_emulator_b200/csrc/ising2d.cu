@@ -19,8 +19,6 @@
 // updated colour once = 2 bits per spin update; the kernel is integer-issue bound, not DRAM bound
 // (see DESIGN.md for the roofline arithmetic).
 
-#include <dlfcn.h>
-
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -32,6 +30,7 @@
 #include "common.cuh"
 #include "philox.cuh"
 #include "ising2d_fast.cuh"
+#include "jit.cuh"
 
 namespace {
 
@@ -608,21 +607,6 @@ unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads -
 // For a launch whose replicas all share one threshold table, ising2d_fast.cuh is compiled once per table set
 // with the eight 5-bit truth tables as literals.  libnvrtc and libcuda are opened with dlopen so that the
 // library has no link-time dependency on them; any failure simply leaves the prebuilt jump-table kernel in use.
-struct JitApi {
-  bool tried = false, ok = false;
-  int (*nvrtcCreateProgram)(void**, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
-  int (*nvrtcCompileProgram)(void*, int, const char* const*) = nullptr;
-  int (*nvrtcGetCUBINSize)(void*, size_t*) = nullptr;
-  int (*nvrtcGetCUBIN)(void*, char*) = nullptr;
-  int (*nvrtcGetProgramLogSize)(void*, size_t*) = nullptr;
-  int (*nvrtcGetProgramLog)(void*, char*) = nullptr;
-  int (*nvrtcDestroyProgram)(void**) = nullptr;
-  int (*cuModuleLoadData)(void**, const void*) = nullptr;
-  int (*cuModuleGetFunction)(void**, void*, const char*) = nullptr;
-  int (*cuLaunchKernel)(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*, void**,
-                        void**) = nullptr;
-};
-JitApi g_jit;
 std::mutex g_jit_mutex;
 std::map<std::string, int> g_jit_cache;  // "device:t0,..,t7" -> handle
 struct JitKernel {
@@ -630,32 +614,6 @@ struct JitKernel {
   int w;  // words per thread it was compiled for
 };
 std::vector<JitKernel> g_jit_functions;  // handle - 1 -> kernel
-
-template <typename F>
-bool jit_sym(void* lib, const char* name, F& fn) {
-  fn = reinterpret_cast<F>(dlsym(lib, name));
-  return fn != nullptr;
-}
-
-bool jit_load_api() {
-  if (g_jit.tried) return g_jit.ok;
-  g_jit.tried = true;
-  void* nv = dlopen("libnvrtc.so", RTLD_NOW | RTLD_LOCAL);
-  if (!nv) nv = dlopen("libnvrtc.so.12", RTLD_NOW | RTLD_LOCAL);
-  void* cu = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
-  if (!nv || !cu) return false;
-  bool ok = jit_sym(nv, "nvrtcCreateProgram", g_jit.nvrtcCreateProgram) &&
-            jit_sym(nv, "nvrtcCompileProgram", g_jit.nvrtcCompileProgram) &&
-            jit_sym(nv, "nvrtcGetCUBINSize", g_jit.nvrtcGetCUBINSize) && jit_sym(nv, "nvrtcGetCUBIN", g_jit.nvrtcGetCUBIN) &&
-            jit_sym(nv, "nvrtcGetProgramLogSize", g_jit.nvrtcGetProgramLogSize) &&
-            jit_sym(nv, "nvrtcGetProgramLog", g_jit.nvrtcGetProgramLog) &&
-            jit_sym(nv, "nvrtcDestroyProgram", g_jit.nvrtcDestroyProgram) &&
-            jit_sym(cu, "cuModuleLoadData", g_jit.cuModuleLoadData) &&
-            jit_sym(cu, "cuModuleGetFunction", g_jit.cuModuleGetFunction) &&
-            jit_sym(cu, "cuLaunchKernel", g_jit.cuLaunchKernel);
-  g_jit.ok = ok;
-  return ok;
-}
 
 JitKernel jit_function(int handle) {
   std::lock_guard<std::mutex> lock(g_jit_mutex);
@@ -717,8 +675,7 @@ int launch_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int
     const unsigned grid = blocks_for(total, 128);
     if (use_jit) {  // table-specialised build of the same kernel body
       void* args[] = {&P};
-      int rc = g_jit.cuLaunchKernel(jit.fn, grid, 1, 1, 128, 1, 1, 0, (void*)st, args, nullptr);
-      if (rc != 0) return 999;  // CUDA_ERROR_UNKNOWN for a driver-API launch failure
+      if (tsu_jit::launch(jit.fn, grid, 128, 0, (void*)st, args) != 0) return 999;  // driver-API launch failure
     } else if (W == 2) {
       half_sweep_fast_kernel<2, 8><<<grid, 128, 0, st>>>(P);
     } else {
@@ -1001,12 +958,12 @@ int tsu_ising2d_jit_prepare(const uint32_t* h_lut, const char* src_dir, char* lo
   TSU_CHECK_ARG(h_lut && src_dir);
   if (log_buf && log_len > 0) log_buf[0] = 0;
   std::lock_guard<std::mutex> lock(g_jit_mutex);
-  if (!jit_load_api()) {
+  if (!tsu_jit::available()) {
     if (log_buf && log_len > 0) snprintf(log_buf, log_len, "libnvrtc.so / libcuda.so.1 not available");
     return 0;
   }
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaFree(0) != cudaSuccess) return 0;  // makes the primary context current
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   unsigned tab[8];
   for (int k = 0; k < 8; ++k) {
     unsigned m = 0;
@@ -1034,30 +991,10 @@ int tsu_ising2d_jit_prepare(const uint32_t* h_lut, const char* src_dir, char* lo
       "#include \"ising2d_fast.cuh\"\n"
       "extern \"C\" __global__ void __launch_bounds__(128, TSU_JIT_MINB) tsu_jit_half_sweep(tsu_fast::SweepParams P) {\n"
       "  tsu_fast::half_sweep_fast_body<TSU_JIT_W>(P);\n}\n";
-  void* prog = nullptr;
-  if (g_jit.nvrtcCreateProgram(&prog, src.c_str(), "tsu_jit.cu", 0, nullptr, nullptr) != 0) return 0;
-  const std::string inc = std::string("-I") + src_dir;
-  const char* opts[] = {"--gpu-architecture=sm_100a", inc.c_str(), "-std=c++17", "-lineinfo"};
-  const int rc = g_jit.nvrtcCompileProgram(prog, 4, opts);
-  if (rc != 0) {
-    size_t n = 0;
-    if (log_buf && log_len > 0 && g_jit.nvrtcGetProgramLogSize(prog, &n) == 0 && n > 1) {
-      std::vector<char> log(n);
-      g_jit.nvrtcGetProgramLog(prog, log.data());
-      snprintf(log_buf, log_len, "%s", log.data());
-    }
-    g_jit.nvrtcDestroyProgram(&prog);
-    g_jit_cache[key] = 0;
-    return 0;
-  }
-  size_t n = 0;
-  g_jit.nvrtcGetCUBINSize(prog, &n);
-  std::vector<char> cubin(n);
-  g_jit.nvrtcGetCUBIN(prog, cubin.data());
-  g_jit.nvrtcDestroyProgram(&prog);
-  void *mod = nullptr, *fn = nullptr;
-  if (g_jit.cuModuleLoadData(&mod, cubin.data()) != 0 || g_jit.cuModuleGetFunction(&fn, mod, "tsu_jit_half_sweep") != 0) {
-    if (log_buf && log_len > 0) snprintf(log_buf, log_len, "cuModuleLoadData / cuModuleGetFunction failed");
+  std::string log;
+  void* fn = tsu_jit::compile(src, "tsu_jit.cu", "tsu_jit_half_sweep", src_dir, log);
+  if (!fn) {
+    if (log_buf && log_len > 0) snprintf(log_buf, log_len, "%s", log.c_str());
     g_jit_cache[key] = 0;
     return 0;
   }

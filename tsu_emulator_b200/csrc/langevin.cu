@@ -13,105 +13,21 @@
 // Parity mode reads the N(0,1) draws from a caller tensor so that the reference (with
 // numpy.random.randn patched to the same draws) can be compared step for step.
 
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
 #include "common.cuh"
-#include "philox.cuh"
+#include "jit.cuh"
+#include "langevin_body.cuh"
 
 namespace {
 
 enum { ENERGY_QUADRATIC = 0, ENERGY_MIXTURE = 1, ENERGY_DOUBLE_WELL = 2, ENERGY_QUADRATIC_FORM = 3 };
 
-constexpr int kMaxDynDim = 64;
-
-struct LangevinParams {
-  void* x;
-  const void* x_init;
-  const void* normals;
-  void* traj;
-  const double* params;
-  long long n_chains;
-  unsigned long long chain0;
-  int dim, energy_kind, n_params;
-  int n_burnin, n_steps;
-  int first_chain_exact;
-  double jitter, drift, noise;  // drift = dt / gamma, noise = sqrt(2 T dt / gamma)
-  uint32_t k0, k1;
-};
-
-__device__ __forceinline__ float lg2_fast(float x) {  // x in [2^-25, 1): no denormal handling needed
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-template <typename real>
-struct BoxMuller;
-
-template <>
-struct BoxMuller<float> {
-  static constexpr int kPerCall = 4;
-  // 4 normals from one Philox block (24-bit uniforms, exactly representable in float)
-  __device__ static __forceinline__ void draw(const tsu_u32x4& o, float z[4]) {
-    const float u1 = ((float)(o.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float u2 = ((float)(o.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float u3 = ((float)(o.z >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float u4 = ((float)(o.w >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    // fast-math forms (MUFU lg2 / rsq / sin / cos, absolute error ~2^-21): the float32 kernel is instruction bound and
-    // the library logf / sincospif cost three times as many instructions as the rest of the step
-    const float a1 = -1.3862943611f * lg2_fast(u1), a2 = -1.3862943611f * lg2_fast(u3);  // -2 ln u > 0 (u < 1)
-    // (u rounds to 1.0f for the top uniforms: a = 0 -> r = 0, guarded against 0 * inf)
-    const float r1 = a1 * rsqrtf(fmaxf(a1, 1e-30f)), r2 = a2 * rsqrtf(fmaxf(a2, 1e-30f));
-    const float t1 = 6.2831853072f * u2, t2 = 6.2831853072f * u4;
-    z[0] = r1 * __cosf(t1);
-    z[1] = r1 * __sinf(t1);
-    z[2] = r2 * __cosf(t2);
-    z[3] = r2 * __sinf(t2);
-  }
-};
-
-template <>
-struct BoxMuller<double> {
-  static constexpr int kPerCall = 2;
-  // 2 normals from one Philox block (53-bit uniforms)
-  __device__ static __forceinline__ void draw(const tsu_u32x4& o, double z[2]) {
-    const unsigned long long a = (((unsigned long long)o.x << 32) | o.y) >> 11;
-    const unsigned long long b = (((unsigned long long)o.z << 32) | o.w) >> 11;
-    const double u1 = ((double)a + 0.5) * (1.0 / 9007199254740992.0);
-    const double u2 = ((double)b + 0.5) * (1.0 / 9007199254740992.0);
-    const double r = sqrt(-2.0 * log(u1));
-    double s, c;
-    sincospi(2.0 * u2, &s, &c);
-    z[0] = r * c;
-    z[1] = r * s;
-  }
-};
-
-// N(0,1) vector for (chain, step): injected rows or Philox + Box-Muller
-template <typename real, int DIM>
-__device__ __forceinline__ void normal_vector(const LangevinParams& P, unsigned long long chain_g, long long chain_l,
-                                              int step, int dim, real* z) {
-  if (P.normals) {
-    const long long rows = 1LL + P.n_burnin + P.n_steps;
-    const real* src = reinterpret_cast<const real*>(P.normals) + ((size_t)chain_l * rows + step) * dim;
-#pragma unroll
-    for (int i = 0; i < (DIM > 0 ? DIM : kMaxDynDim); ++i)
-      if (i < dim) z[i] = src[i];
-    return;
-  }
-  constexpr int PER = BoxMuller<real>::kPerCall;
-  constexpr int MAXD = DIM > 0 ? DIM : kMaxDynDim;
-#pragma unroll
-  for (int b = 0; b < (MAXD + PER - 1) / PER; ++b) {
-    if (b * PER < dim) {
-      tsu_u32x4 o = tsu_philox4x32_10((uint32_t)chain_g, ((uint32_t)(chain_g >> 32) & 0xFFFFu) | ((uint32_t)b << 16),
-                                      (uint32_t)step, TSU_STREAM_LANGEVIN, P.k0, P.k1);
-      real t[PER];
-      BoxMuller<real>::draw(o, t);
-#pragma unroll
-      for (int q = 0; q < PER; ++q)
-        if (b * PER + q < MAXD && b * PER + q < dim) z[b * PER + q] = t[q];
-    }
-  }
-}
+using tsu_langevin::kMaxDynDim;
+using tsu_langevin::LangevinParams;
 
 // gradient of the built-in energies; sp = parameters staged in shared memory as `real`
 template <typename real, int DIM>
@@ -170,50 +86,21 @@ __device__ __forceinline__ void gradient(int kind, int dim, const real* __restri
 }
 
 template <typename real, int DIM>
+struct BuiltinGrad {
+  int kind;
+  const real* sp;
+  __device__ __forceinline__ void operator()(int dim, const real* x, real* g) const {
+    gradient<real, DIM>(kind, dim, sp, x, g);
+  }
+};
+
+template <typename real, int DIM>
 __global__ void __launch_bounds__(128) langevin_kernel(LangevinParams P) {
   extern __shared__ double smem_raw[];
   real* sp = reinterpret_cast<real*>(smem_raw);
   for (int i = threadIdx.x; i < P.n_params; i += blockDim.x) sp[i] = (real)P.params[i];
   __syncthreads();
-
-  const long long chain = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (chain >= P.n_chains) return;
-  const unsigned long long chain_g = P.chain0 + (unsigned long long)chain;
-  const int dim = DIM > 0 ? DIM : P.dim;
-  constexpr int MAXD = DIM > 0 ? DIM : kMaxDynDim;
-  real x[MAXD], z[MAXD], g[MAXD];
-
-  const real* xi = reinterpret_cast<const real*>(P.x_init);
-#pragma unroll
-  for (int i = 0; i < MAXD; ++i)
-    if (i < dim) x[i] = xi ? xi[i] : (real)0;
-  // every chain but the first of a call starts at x_init + jitter * N(0, I)  (core.py:142-143)
-  if (!(chain == 0 && P.first_chain_exact) && P.jitter != 0.0) {
-    normal_vector<real, DIM>(P, chain_g, chain, 0, dim, z);
-#pragma unroll
-    for (int i = 0; i < MAXD; ++i)
-      if (i < dim) x[i] = x[i] + (real)P.jitter * z[i];
-  }
-  const real drift = (real)P.drift, noise = (real)P.noise;
-  const int total = P.n_burnin + P.n_steps;
-  real* traj = reinterpret_cast<real*>(P.traj);
-  for (int s = 0; s < total; ++s) {
-    gradient<real, DIM>(P.energy_kind, dim, sp, x, g);
-    normal_vector<real, DIM>(P, chain_g, chain, s + 1, dim, z);
-#pragma unroll
-    for (int i = 0; i < MAXD; ++i)
-      if (i < dim) x[i] = x[i] + (-g[i] * drift) + noise * z[i];  // core.py:74-80 order of operations
-    if (traj && s >= P.n_burnin) {
-      real* dst = traj + ((size_t)chain * P.n_steps + (s - P.n_burnin)) * dim;
-#pragma unroll
-      for (int i = 0; i < MAXD; ++i)
-        if (i < dim) dst[i] = x[i];
-    }
-  }
-  real* out = reinterpret_cast<real*>(P.x) + (size_t)chain * dim;
-#pragma unroll
-  for (int i = 0; i < MAXD; ++i)
-    if (i < dim) out[i] = x[i];
+  tsu_langevin::langevin_chain<real, DIM>(P, BuiltinGrad<real, DIM>{P.energy_kind, sp});
 }
 
 template <typename real, int DIM>
@@ -278,4 +165,79 @@ extern "C" int tsu_langevin_run(void* d_x, int dtype, int64_t n_chains, int dim,
   P.k0 = (uint32_t)seed;
   P.k1 = (uint32_t)(seed >> 32);
   return dtype == 0 ? dispatch_dim<float>(P, tsu_stream(stream)) : dispatch_dim<double>(P, tsu_stream(stream));
+}
+
+
+// ---- traced Python energies: the gradient arrives as CUDA source (tsu_emulator_b200/trace.py) -------------------
+namespace {
+struct LangevinJit {
+  void* fn;
+  int dtype, dim;
+};
+std::mutex g_lj_mutex;
+std::map<std::string, int> g_lj_cache;
+std::vector<LangevinJit> g_lj;
+}  // namespace
+
+extern "C" int tsu_langevin_jit_prepare(const char* grad_source, int dtype, int dim, const char* src_dir, char* log_buf,
+                                        int log_len) {
+  TSU_CHECK_ARG(grad_source && src_dir && (dtype == 0 || dtype == 1) && dim > 0 && dim <= kMaxDynDim);
+  if (log_buf && log_len > 0) log_buf[0] = 0;
+  std::lock_guard<std::mutex> lock(g_lj_mutex);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  const std::string key = std::to_string(dev) + ":" + std::to_string(dtype) + ":" + std::to_string(dim) + ":" + grad_source;
+  auto it = g_lj_cache.find(key);
+  if (it != g_lj_cache.end()) return it->second;
+  std::string src = "#include \"langevin_body.cuh\"\n";
+  src += grad_source;
+  src += "\nstruct TsuUserGrad {\n  template <typename real>\n  __device__ __forceinline__ void operator()(int, const real* x, "
+         "real* g) const { tsu_user_grad<real>(x, g); }\n};\n";
+  src += std::string("extern \"C\" __global__ void __launch_bounds__(128) tsu_jit_langevin(tsu_langevin::LangevinParams P) {\n") +
+         "  tsu_langevin::langevin_chain<" + (dtype == 0 ? "float" : "double") + ", " + std::to_string(dim) +
+         ">(P, TsuUserGrad());\n}\n";
+  std::string log;
+  void* fn = tsu_jit::compile(src, "tsu_jit_langevin.cu", "tsu_jit_langevin", src_dir, log);
+  if (!fn) {
+    if (log_buf && log_len > 0) snprintf(log_buf, log_len, "%s", log.c_str());
+    g_lj_cache[key] = 0;
+    return 0;
+  }
+  g_lj.push_back(LangevinJit{fn, dtype, dim});
+  const int handle = (int)g_lj.size();
+  g_lj_cache[key] = handle;
+  return handle;
+}
+
+extern "C" int tsu_langevin_run_jit(int handle, void* d_x, int64_t n_chains, const void* d_x_init, double jitter,
+                                    int first_chain_exact, double T, double dt, double gamma, int n_burnin, int n_steps,
+                                    uint64_t seed, uint64_t chain0, const void* d_normals, void* d_traj, uintptr_t stream) {
+  LangevinJit k;
+  {
+    std::lock_guard<std::mutex> lock(g_lj_mutex);
+    TSU_CHECK_ARG(handle >= 1 && handle <= (int)g_lj.size());
+    k = g_lj[handle - 1];
+  }
+  TSU_CHECK_ARG(d_x && n_chains > 0 && T > 0 && dt > 0 && gamma > 0 && n_burnin >= 0 && n_steps >= 0);
+  LangevinParams P;
+  P.x = d_x;
+  P.x_init = d_x_init;
+  P.normals = d_normals;
+  P.traj = d_traj;
+  P.params = nullptr;
+  P.n_chains = n_chains;
+  P.chain0 = chain0;
+  P.dim = k.dim;
+  P.energy_kind = -1;
+  P.n_params = 0;
+  P.n_burnin = n_burnin;
+  P.n_steps = n_steps;
+  P.jitter = jitter;
+  P.first_chain_exact = first_chain_exact;
+  P.drift = dt / gamma;
+  P.noise = sqrt(2.0 * T * dt / gamma);
+  P.k0 = (uint32_t)seed;
+  P.k1 = (uint32_t)(seed >> 32);
+  void* args[] = {&P};
+  return tsu_jit::launch(k.fn, (unsigned)((n_chains + 127) / 128), 128, 0, (void*)tsu_stream(stream), args);
 }

@@ -427,11 +427,21 @@ class IsingModel2D:
             self.engine.set_spins(initial_state)
         else:
             self.engine.init_random()
+        self._obs_at = None   # sweep index the cached observables belong to
+        self._obs = None
 
     def gibbs_update(self, n_sweeps: int = 1):
         """one full heat-bath sweep (black then white sublattice)"""
         self.engine.sweep(n_sweeps)
         return self
+
+    def _observables(self):
+        """(# up spins, # anti-aligned bonds) of the current lattice: ONE kernel launch and one device-to-host copy
+        serve magnetization() and energy() until the lattice is updated again"""
+        if self._obs_at != self.engine.sweep_index:
+            self._obs = self.engine.observables_tensor().cpu().numpy().astype(np.float64)
+            self._obs_at = self.engine.sweep_index
+        return self._obs
 
     def equilibrate(self, temperature: Optional[float] = None, n_sweeps: Optional[int] = None):
         """set the temperature and run n_burnin (default 100, IsingConfig.n_burnin) sweeps; chainable"""
@@ -445,12 +455,14 @@ class IsingModel2D:
 
     def magnetization(self):
         """signed magnetisation per spin of the current lattice (array if n_replicas > 1)"""
-        m = self.engine.magnetization()
+        eng = self.engine
+        m = (2.0 * self._observables()[:, 0] - eng.n_sites) / eng.n_sites
         return float(m[0]) if m.size == 1 else m
 
     def energy(self):
         """total energy of the current lattice"""
-        e = self.engine.energy()
+        eng, obs = self.engine, self._observables()
+        e = -eng.coupling * (eng.n_bonds - 2.0 * obs[:, 1]) - eng.field * (2.0 * obs[:, 0] - eng.n_sites)
         return float(e[0]) if e.size == 1 else e
 
     @property
