@@ -215,14 +215,20 @@ int tsu_dense_energy(const void* d_Jt, int j_dtype, const void* d_bias, const ui
 int tsu_dense_init_random(uint8_t* d_state, int n_chains, int N, uint64_t seed, uint32_t chain0,
                           uintptr_t stream);
 
-/* Batched dense-J Gibbs sweeps on the tensor cores (BASELINE config 3).  Same sequential heat-bath rule as
- * tsu_dense_gibbs_run (sites 0..N-1 in order, every update sees all earlier ones), evaluated in blocks of 64
- * sites: the block's fields for 128 chains are a 128 x 64 x N tcgen05 GEMM (bf16 J and 0/1 spins, fp32
- * accumulation in TMEM), the in-block dependence is resolved exactly by rank-1 corrections.
+/* Batched dense-J Gibbs sweeps on the tensor cores (BASELINE config 3; csrc/dense_tc.cu).  Same sequential
+ * heat-bath rule as tsu_dense_gibbs_run (sites 0..N-1 in order, every update sees all earlier ones), blocked on two
+ * levels: per 128-site PANEL the fields of a CTA's 128 (or 64) chains are one M x 128 x N tcgen05 GEMM (bf16 J by
+ * TMA with 128-byte swizzle, spins expanded to bf16 0 / 2 straight into tensor memory, fp32 accumulation in TMEM);
+ * per 32-site BLOCK the sites are walked in registers with rank-1 corrections, and one small MMA carries the
+ * block's flips to the rest of the panel.  Identical to the site-by-site sweep for the same fields.
  *   d_J_bf16: [N][N] row-major bf16, row i = couplings into site i (J itself, not the transpose);
- *   d_bias: [N] float32 or NULL; d_state: [n_chains][N] uint8 bits in place; N % 128 == 0, N <= 4096.
+ *   d_bias: [N] float32 or NULL; d_state: [n_chains][N] uint8 bits in place; N % 128 == 0, N <= 4096
+ *   (the host mirror pads other sizes with uncoupled sites).
  *   Uniform of (site, chain, sweep): 24 bits of word (site & 3) of Philox(counter = (site >> 2,
- *   chain0 + chain, sweep0 + sweep, 'DENT')), compared in fp32 with sigmoid(h/T) (clamped at |x| > 20).
+ *   chain0 + chain, sweep0 + sweep, 'DENT')).  Acceptance  u < sigmoid(h/T)  is evaluated as  h > T * logit(u)
+ *   (strict; thresholds clamped to +-20 T = the reference's sigmoid clamp) with logit(u) from lg2.approx in fp32:
+ *   against the float64 rule it can only disagree where |u - sigmoid(h/T)| < ~5e-6 for exactly representable
+ *   couplings, ~5e-5 for Gaussian couplings up to N = 4096 (counted and bounded by tests/test_dense_gpu.py).
  *   d_fields_or_null: [n_chains][N] float32, diagnostics: the field of every site as the kernel compares it on
  *   its last visit (the local field minus J[i][i'] for the earlier sites i' of the same 32-site block that were 1
  *   before the visit; that part is folded into the acceptance threshold). */

@@ -12,7 +12,7 @@ What it follows in the reference (/root/reference, read-only):
   * bit bias                 tsu/models/ising.py:140-148 (reference: -2h + 2 rowsum(J); see `bias_mode`)
   * energy / magnetisation   tsu/models/ising.py:98-117,183-193
 
-Parity pinning: tests/test_oracle_vs_reference.py drives the UNMODIFIED reference
+Parity pinning: tests/test_oracle_lattice.py drives the UNMODIFIED reference
 `GibbsSampler.gibbs_sweep` (update_order="random", numpy.random.permutation patched to
 black-then-white order, numpy.random.rand patched to the injected uniforms) and checks
 bit equality with `checkerboard_sweeps` below; the same script writes tests/golden/*.npz.

@@ -4,7 +4,9 @@ Build libtsu_b200.so (the C-ABI library) in-tree with nvcc for sm_100a.
     python -m tsu_emulator_b200.build [--force] [--verbose]
 
 nvcc cross-compiles without a GPU.  The .so is git-ignored but travels to the GPU box with the
-gpurun snapshot; nothing is JIT-compiled at run time.
+gpurun snapshot.  Two kernels are additionally specialised at run time with NVRTC (csrc/jit.cu): the lattice
+half-sweep for one temperature's threshold tables, and the Langevin chain loop for traced Python energies; both have
+prebuilt counterparts in the .so and fall back to them (lattice) or raise (traced energies) where NVRTC is missing.
 """
 
 import hashlib

@@ -1,4 +1,4 @@
-// Dense-coupling Gibbs sampler on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+// Dense-coupling Gibbs sampler on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
 //
 // Replaces, for a batch of chains that share one coupling matrix (BASELINE config 3: N = 4096 spins,
 // 2048 chains), the local-field evaluation of the reference
@@ -6,24 +6,35 @@
 // inside the sequential sweep of tsu/gibbs.py:128-162.
 //
 // Exact sequential Gibbs, blocked on two levels.  The N sites are visited in index order.
-//   * PANEL (128 sites): the fields of a panel's sites for 128 chains are one 128 x 128 x N GEMM
+//   * PANEL (128 sites): the fields of a panel's sites for the CTA's chains are one M x 128 x N GEMM
 //     H = S . J[panel, :]^T  (S: current bits as bf16, J: bf16, fp32 accumulation in TMEM), issued as
-//     tcgen05.mma M128 N128 K16 instructions by one thread.  The K-chunk that holds the previous panel is
-//     multiplied last, after that panel's update; all other chunks overlap with it.
+//     tcgen05.mma M128 (or M64) N128 K16 instructions by one elected thread.  The K-chunk that holds the previous
+//     panel is multiplied last, after that panel's update; all other chunks overlap with it.
 //   * BLOCK (32 sites, four per panel): the epilogue thread of each chain reads the block's 32 fields out of
 //     TMEM, walks the sites in order, draws the heat-bath bit and applies the rank-1 correction
-//     h_i' += J[i', i] * (new - old) to the not yet visited sites of the block in registers.  The flips of the
-//     block are then written to TMEM as a 128 x 32 operand (-1 / 0 / +1) and ONE small MMA
+//     h_i' += J[i', i] * new_i to the not yet visited sites of the block in registers (the "- J old" half of
+//     the correction is folded into the acceptance thresholds ahead of time).  The flips of the block are then
+//     written to TMEM as an M x 32 operand (-2 / 0 / +2) and ONE small MMA
 //     H[:, later blocks of the panel] += delta . J[later, block]^T  corrects the rest of the panel.
 // The result is identical to a site-by-site sweep with the same fields.
 //
-// One CTA owns 128 chains (TMEM lane = chain).  The chain states stay resident in shared memory as bits
-// for the whole sweep (64 KB).  Each K-chunk of 128 sites is expanded to bf16 by the thread that owns the
-// chain and written straight into TENSOR MEMORY (tcgen05.st, lane = chain, column = K pair): the spin
-// operand A never touches shared memory.  A spin is encoded as 0.0 / 2.0: bf16 2.0 = 0x4000 has ONE set bit,
-// so a packed pair of spins is (word << s) & 0x40004000 - two integer instructions per register - and the
-// accumulated field is halved (exactly) in the epilogue.  The matching J tile (operand B, 128 x 128, K-major,
-// no swizzle) is streamed from L2 with cp.async.
+// One CTA owns M = 128 chains (TMEM lane = chain), or 64 when there are too few chains to give every SM a tile.
+// The chain states stay resident in shared memory as bits for the whole call.  Each K-chunk of 128 sites is
+// expanded to bf16 by the thread that owns the chain and written straight into TENSOR MEMORY (tcgen05.st,
+// lane = chain, column = K pair): the spin operand A never touches shared memory.  A spin is encoded as 0.0 / 2.0:
+// bf16 2.0 = 0x4000 has ONE set bit, so a packed pair of spins is (word << s) & 0x40004000 - two integer
+// instructions per register - and the accumulated field is halved (exactly) in the epilogue.  The matching J
+// tile (operand B, 128 x 128, K-major) is fetched by TMA (cp.async.bulk.tensor.2d, two 64-column boxes with the
+// 128-byte swizzle the UMMA descriptor expects) into a 3-stage ring; J (32 MB at N = 4096) stays L2-resident.
+//
+// Acceptance: u < sigmoid(h / T)  <=>  h > T * logit(u) (strict, gibbs.py:126), thresholds T * logit(u) clamped to
+// +-20 T (the reference's sigmoid clamp, gibbs.py:65-70), u = 24-bit Philox uniform, logit via lg2.approx in fp32,
+// produced one block ahead by two dedicated warps.  Against the float64 rule the kernel can only disagree where u
+// lies within ~5e-6 (exactly representable J) / ~5e-5 (Gaussian J, N <= 4096) of the acceptance probability; the
+// tests count those sites and check the bound (tests/test_dense_gpu.py).
+//
+// Warp roles (16 warps): 0-7 two producer groups (TMA requests + spin expansion), 8-11 epilogue, 12 main MMA
+// issuer, 13 in-panel correction issuer, 14-15 thresholds.
 
 #include <cstdlib>
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
@@ -160,6 +171,12 @@ __device__ unsigned long long g_tc_timing[32];
 #define TC_ACC(i) do {} while (0)
 #endif
 
+#ifdef TSU_TC_DEBUG_SWITCHES
+#define TC_DBG(P, bit) ((P).dbg & (bit))
+#else
+#define TC_DBG(P, bit) 0
+#endif
+
 struct TcParams {
   const __nv_bfloat16* J;   // [N][N] row-major coupling matrix (row i = couplings INTO site i)
   const float* bias;        // [N] or nullptr
@@ -170,7 +187,7 @@ struct TcParams {
   float T;
   uint32_t k0, k1, sweep0, chain0;
   int gemm_only;            // diagnostics: no spin update (fields of the initial state for every site)
-  int dbg;                  // diagnostics (TSU_TC_DEBUG, timing experiments only): 1 no MMA, 2 no A expansion, 4 no J loads
+  int dbg;                  // knock-out switches of timing experiments; always 0 unless built with -DTSU_TC_DEBUG_SWITCHES
 };
 
 constexpr int kProducers = 128 * kGroups;           // warps 0-7: 4 warps (128 chains) per group
@@ -321,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
           }
           TC_T0();
           if ((tid & (kChains - 1)) == 0) {  // J[panel p rows, chunk kc columns]: two 16 KB boxes, bytes counted on the stage's full barrier
-            if (P.dbg & 4) {
+            if (TC_DBG(P, 4)) {
               mbar_arrive(&sm.full[s]);
             } else {
               mbar_arrive_expect_tx(&sm.full[s], kTileBytes);
@@ -339,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
           // 128 bits of this chain -> 64 packed bf16 pairs -> 64 TMEM columns of the chain's lane
           const uint32_t a_col = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kAccCols + s * kACols);
 #pragma unroll
-          for (int w4 = 0; w4 < kKC / 32 && !(P.dbg & 2); ++w4) {
+          for (int w4 = 0; w4 < kKC / 32 && !(TC_DBG(P, 2)); ++w4) {
             const uint32_t w = sm.sbits[(kKC / 32) * kc + w4][row];
             uint32_t r[16];
 #pragma unroll
@@ -392,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
           const uint64_t bd0 = b_desc0 + (uint64_t)((uint32_t)s * kSlotUnits);
           const uint32_t a0 = tmem_d + (uint32_t)(kAccCols + s * kACols);
 #pragma unroll
-          for (int j = 0; j < kKC / 16 && !(P.dbg & 1); ++j)
+          for (int j = 0; j < kKC / 16 && !(TC_DBG(P, 1)); ++j)
             umma_bf16_ts(d0, a0 + 8u * j, bd0 + (uint64_t)(((j >> 2) * kHalfBytes + (j & 3) * 32) >> 4), idesc,
                          (cc > 0 || j > 0) ? 1u : 0u);
           umma_commit(&sm.empty[s]);
@@ -457,9 +474,9 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
 #pragma unroll
         for (int c = 0; c < kPer; ++c) {
 #pragma unroll
-          for (int i = 0; i < kBlk && (P.dbg & 16); ++i) v[c][i] = 0.0f;
+          for (int i = 0; i < kBlk && (TC_DBG(P, 16)); ++i) v[c][i] = 0.0f;
 #pragma unroll
-          for (int i = 0; i < kBlk && !(P.dbg & 16); i += 4) {
+          for (int i = 0; i < kBlk && !(TC_DBG(P, 16)); i += 4) {
             const tsu_u32x4 o = tsu_philox4x32_10((uint32_t)((i0 + i) >> 2), cg[c], P.sweep0 + (uint32_t)sweep,
                                                   TSU_STREAM_DENSE_TC, P.k0, P.k1);
             const uint32_t r4[4] = {o.x, o.y, o.z, o.w};
@@ -471,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
             }
           }
         }
-        if (kPrepassAhead && !(P.dbg & 32)) {
+        if (kPrepassAhead && !(TC_DBG(P, 32))) {
           // the "- J old" half of the in-block correction moves to the threshold side (see the epilogue)
           mbar_wait(&sm.jblk_ready, (uint32_t)(gblk & 1));
           const uint32_t w_old = sm.sbits[4 * p + (gblk & 3)][t];
@@ -604,7 +621,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
             w_new |= up ? (1u << site_bit(i)) : 0u;
             // not yet visited sites of the block see the new value (rank-1 correction, branch free)
 #pragma unroll
-            for (int ip = i + 1; ip < kBlk && !(P.dbg & 8); ++ip) h[ip] = fmaf(sm.jblk[jb][i][ip], s_new, h[ip]);
+            for (int ip = i + 1; ip < kBlk && !(TC_DBG(P, 8)); ++ip) h[ip] = fmaf(sm.jblk[jb][i][ip], s_new, h[ip]);
           }
           if (chain_lane_active<kM>(t128)) sm.sbits[blk][row] = w_new;
           TC_B(29);
@@ -685,7 +702,7 @@ static int launch_tc(const TcParams& P, cudaStream_t st) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
   int m = (P.n_chains + 127) / 128 < sm_count ? 64 : 128;
-  if (const char* env = getenv("TSU_TC_M")) m = atoi(env) == 64 ? 64 : 128;
+  if (const char* env = getenv("TSU_TC_M")) m = atoi(env) == 64 ? 64 : 128;  // tile height override (tests; same bits)
   cudaError_t e;
   if (m == 64) {
     e = cudaFuncSetAttribute(dense_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -720,7 +737,9 @@ extern "C" int tsu_dense_gibbs_tc_run(const void* d_J_bf16, const float* d_bias,
   P.sweep0 = sweep0;
   P.chain0 = chain0;
   P.gemm_only = 0;
+#ifdef TSU_TC_DEBUG_SWITCHES  // knock-out timing experiments (tools/tc_dbg.py); results are wrong with any bit set
   if (const char* e = getenv("TSU_TC_DEBUG")) P.dbg = atoi(e);
+#endif
   return launch_tc(P, tsu_stream(stream));
 }
 
@@ -746,6 +765,8 @@ extern "C" int tsu_dense_tc_debug_fields(const void* d_J_bf16, const uint8_t* d_
   P.n_sweeps = 1;
   P.T = 1.0f;
   P.gemm_only = 1;
+#ifdef TSU_TC_DEBUG_SWITCHES  // knock-out timing experiments (tools/tc_dbg.py); results are wrong with any bit set
   if (const char* e = getenv("TSU_TC_DEBUG")) P.dbg = atoi(e);
+#endif
   return launch_tc(P, tsu_stream(stream));
 }
