@@ -39,6 +39,16 @@ class IsingConfig:
             raise ValueError("Temperature must be positive")
 
 
+def _resolve_compat_bias(flag: Optional[bool]) -> bool:
+    """explicit argument, else the process-wide switch TSU_COMPAT_REFERENCE_BIAS=1 (run code written against the
+    reference with the reference's spin-to-bit bias, ising.py:140-148, without touching it), else the correct bias"""
+    if flag is not None:
+        return bool(flag)
+    import os
+
+    return os.environ.get("TSU_COMPAT_REFERENCE_BIAS", "0") not in ("", "0")
+
+
 class IsingModel:
     """General Ising model on an arbitrary graph (tsu/models/ising.py:39-262).
 
@@ -47,7 +57,8 @@ class IsingModel:
     """
 
     def __init__(self, n_spins: Optional[int] = None, config: Optional[IsingConfig] = None, *, J=None, h=None,
-                 temperature: Optional[float] = None, compat_reference_bias: bool = False, seed: Optional[int] = None):
+                 temperature: Optional[float] = None, compat_reference_bias: Optional[bool] = None,
+                 seed: Optional[int] = None):
         if n_spins is None:
             if J is None:
                 raise ValueError("give n_spins or a coupling matrix J")
@@ -56,7 +67,7 @@ class IsingModel:
         if config is None:
             config = IsingConfig(temperature=temperature) if temperature is not None else IsingConfig()
         self.config = config
-        self.compat_reference_bias = bool(compat_reference_bias)
+        self.compat_reference_bias = _resolve_compat_bias(compat_reference_bias)
         # subclasses that know their wiring (IsingChain, IsingGrid) build the dense matrix only on demand
         self._J = None if getattr(self, "_lazy", False) else np.zeros((self.n_spins, self.n_spins))
         self.h = np.ones(self.n_spins) * self.config.external_field
@@ -276,14 +287,15 @@ class IsingGrid(IsingModel):
     """
 
     def __init__(self, size: Tuple[int, int], J: float = 1.0, config: Optional[IsingConfig] = None,
-                 periodic: bool = False, *, compat_reference_bias: bool = False, seed: Optional[int] = None):
+                 periodic: bool = False, *, compat_reference_bias: Optional[bool] = None,
+                 seed: Optional[int] = None):
         self.rows, self.cols = size
         self.periodic = periodic
         self.coupling = float(J)
         n_spins = self.rows * self.cols
         self.n_spins = n_spins
         self.config = config or IsingConfig()
-        self.compat_reference_bias = bool(compat_reference_bias)
+        self.compat_reference_bias = _resolve_compat_bias(compat_reference_bias)
         self._J = None  # dense matrix built on demand only
         self.h = np.ones(n_spins) * self.config.external_field
         self._seed = int(seed) if seed is not None else int(np.random.randint(0, 2**31 - 1))
