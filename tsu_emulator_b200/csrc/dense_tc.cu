@@ -37,6 +37,7 @@
 // issuer, 13 in-panel correction issuer, 14-15 thresholds.
 
 #include <cstdlib>
+#include <type_traits>
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 
@@ -227,6 +228,45 @@ struct TcSmem {
   __align__(8) uint64_t corr_done;           // correction issuer -> epilogue: the rest of the panel is corrected (commit)
   uint32_t tmem_base;
 };
+
+// acc[ip] += row[ip] * s for ip = first .. 31 (the rank-1 corrections of the sequential block update) with the packed
+// dual-fp32 FMA of sm_100 (fma.rn.f32x2 -> FFMA2: two IEEE fp32 FMAs per instruction, same rounding as fmaf): half the
+// instructions on the pipe the epilogue shares with everybody else.  `row` is a 16-byte aligned shared-memory row.
+__device__ __forceinline__ void ffma2(float& a0, float& a1, float j0, float j1, unsigned long long ss) {
+  unsigned long long jj, aa;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(jj) : "f"(j0), "f"(j1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a0), "f"(a1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(aa) : "l"(jj), "l"(ss));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(aa));
+}
+
+template <int kFirst>
+__device__ __forceinline__ void axpy_tail(float (&acc)[32], const float* __restrict__ row, float s) {
+  if constexpr ((kFirst & 1) != 0) acc[kFirst] = fmaf(row[kFirst], s, acc[kFirst]);
+  constexpr int kPair0 = (kFirst + 1) & ~1;       // first even index
+  constexpr int kQuad0 = (kPair0 + 3) & ~3;       // first index that is a multiple of 4
+  unsigned long long ss;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ss) : "f"(s));
+  if constexpr (kPair0 < kQuad0 && kPair0 < 32) {  // one 8-byte load up to the 16-byte boundary
+    const float2 j2 = *reinterpret_cast<const float2*>(row + kPair0);
+    ffma2(acc[kPair0], acc[kPair0 + 1], j2.x, j2.y, ss);
+  }
+#pragma unroll
+  for (int ip = kQuad0; ip < 32; ip += 4) {       // 16-byte loads: one LDS.128 feeds two FFMA2
+    const float4 j4 = *reinterpret_cast<const float4*>(row + ip);
+    ffma2(acc[ip], acc[ip + 1], j4.x, j4.y, ss);
+    ffma2(acc[ip + 2], acc[ip + 3], j4.z, j4.w, ss);
+  }
+}
+
+// compile-time loop over the 32 sites of a block: f(integral_constant<i>)
+template <int I, typename F>
+__device__ __forceinline__ void for_each_site(F&& f) {
+  if constexpr (I < 32) {
+    f(std::integral_constant<int, I>{});
+    for_each_site<I + 1>(f);
+  }
+}
 
 // log2 without the denormal pre-scaling of __log2f (the arguments are 0 or >= 2^-24)
 __device__ __forceinline__ float lg2_ftz(float x) {
@@ -492,12 +532,11 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
           // the "- J old" half of the in-block correction moves to the threshold side (see the epilogue)
           mbar_wait(&sm.jblk_ready, (uint32_t)(gblk & 1));
           const uint32_t w_old = sm.sbits[4 * p + (gblk & 3)][t];
-#pragma unroll
-          for (int i = 0; i < kBlk; ++i) {
+          for_each_site<0>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
             const float old_i = ((w_old >> site_bit(i)) & 1u) ? 1.0f : 0.0f;
-#pragma unroll
-            for (int ip = i + 1; ip < kBlk; ++ip) v[0][ip] = fmaf(sm.jblk[gblk & 1][i][ip], old_i, v[0][ip]);
-          }
+            axpy_tail<i + 1>(v[0], sm.jblk[gblk & 1][i], old_i);
+          });
         }
         if (gblk > 0) mbar_wait(&sm.thr_free, (uint32_t)((gblk - 1) & 1));  // the previous block's thresholds are in registers
 #pragma unroll
@@ -567,12 +606,11 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
 #pragma unroll
           for (int i = 0; i < kBlk; ++i) thr[i] = sm.thr[i][row];
           if (!kPrepassAhead) {
-#pragma unroll
-            for (int i = 0; i < kBlk; ++i) {
+            for_each_site<0>([&](auto ic) {
+              constexpr int i = decltype(ic)::value;
               const float old_i = ((w_old >> site_bit(i)) & 1u) ? 1.0f : 0.0f;
-#pragma unroll
-              for (int ip = i + 1; ip < kBlk; ++ip) thr[ip] = fmaf(sm.jblk[jb][i][ip], old_i, thr[ip]);
-            }
+              axpy_tail<i + 1>(thr, sm.jblk[jb][i], old_i);
+            });
           }
           warp_arrive(&sm.thr_free);
         }
@@ -613,16 +651,15 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
           // sequential heat-bath update of the 32 sites of this block for this thread's chain (gibbs.py:153-160)
           static_assert(kBlk == 32, "one state word per block");
           uint32_t w_new = 0;
-#pragma unroll
-          for (int i = 0; i < kBlk; ++i) {
+          for_each_site<0>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
             if (P.fields_out && chain_ok) P.fields_out[(size_t)chain * N + i0 + i] = h[i];  // as compared (diagnostics)
             const bool up = h[i] > thr[i];
             const float s_new = up ? 1.0f : 0.0f;
             w_new |= up ? (1u << site_bit(i)) : 0u;
             // not yet visited sites of the block see the new value (rank-1 correction, branch free)
-#pragma unroll
-            for (int ip = i + 1; ip < kBlk && !(TC_DBG(P, 8)); ++ip) h[ip] = fmaf(sm.jblk[jb][i][ip], s_new, h[ip]);
-          }
+            if (!(TC_DBG(P, 8))) axpy_tail<i + 1>(h, sm.jblk[jb][i], s_new);
+          });
           if (chain_lane_active<kM>(t128)) sm.sbits[blk][row] = w_new;
           TC_B(29);
           if (b < 3) {
