@@ -229,9 +229,8 @@ int tsu_dense_init_random(uint8_t* d_state, int n_chains, int N, uint64_t seed, 
  *   (strict; thresholds clamped to +-20 T = the reference's sigmoid clamp) with logit(u) from lg2.approx in fp32:
  *   against the float64 rule it can only disagree where |u - sigmoid(h/T)| < ~5e-6 for exactly representable
  *   couplings, ~5e-5 for Gaussian couplings up to N = 4096 (counted and bounded by tests/test_dense_gpu.py).
- *   d_fields_or_null: [n_chains][N] float32, diagnostics: the field of every site as the kernel compares it on
- *   its last visit (the local field minus J[i][i'] for the earlier sites i' of the same 32-site block that were 1
- *   before the visit; that part is folded into the acceptance threshold). */
+ *   d_fields_or_null: [n_chains][N] float32, diagnostics: the local field of every site as the kernel compares it on
+ *   its last visit. */
 int tsu_dense_gibbs_tc_run(const void* d_J_bf16, const float* d_bias, uint8_t* d_state, int n_chains,
                            int N, double T, const double* d_T_chain, int n_sweeps, uint64_t seed,
                            uint32_t sweep0, uint32_t chain0, float* d_fields_or_null, uintptr_t stream);

@@ -12,8 +12,8 @@
 //     panel is multiplied last, after that panel's update; all other chunks overlap with it.
 //   * BLOCK (32 sites, four per panel): the epilogue thread of each chain reads the block's 32 fields out of
 //     TMEM, walks the sites in order, draws the heat-bath bit and applies the rank-1 correction
-//     h_i' += J[i', i] * new_i to the not yet visited sites of the block in registers (the "- J old" half of
-//     the correction is folded into the acceptance thresholds ahead of time).  The flips of the block are then
+//     h_i' += J[i', i] * (new_i - old_i) to the not yet visited sites of the block in registers (packed dual-fp32
+//     FMAs, fma.rn.f32x2 -> FFMA2: the chain is bound by the FMA pipe).  The flips of the block are then
 //     written to TMEM as an M x 32 operand (-2 / 0 / +2) and ONE small MMA
 //     H[:, later blocks of the panel] += delta . J[later, block]^T  corrects the rest of the panel.
 // The result is identical to a site-by-site sweep with the same fields.
@@ -222,7 +222,6 @@ struct TcSmem {
   __align__(8) uint64_t panel_done[4];       // epilogue -> producers: bits of panel gp written (ring, one arrival per warp)
   __align__(8) uint64_t delta_ready;         // epilogue -> correction issuer: flips of a block are in TMEM (per warp)
   __align__(8) uint64_t thr_full;            // threshold warps -> epilogue: thresholds of the next block written (per warp)
-  __align__(8) uint64_t jblk_ready;          // epilogue -> threshold warps: jblk of the next block is staged     (per warp)
   __align__(8) uint64_t thr_free;            // epilogue -> threshold warps: thresholds are in registers       (per warp)
   __align__(8) uint64_t jdiag_full;          // TMA -> correction issuer: jdiag of the panel landed
   __align__(8) uint64_t corr_done;           // correction issuer -> epilogue: the rest of the panel is corrected (commit)
@@ -307,7 +306,6 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
   const int tid = threadIdx.x, warp = tid >> 5;
   const int N = P.N;
   const int n_panels = N / kPanel;  // = number of K-chunks
-  constexpr bool kPrepassAhead = (kM == 64);  // who folds the old spins into the thresholds (see the epilogue)
   const int total_panels = n_panels * P.n_sweeps;
 
   // ---- one-time setup -------------------------------------------------------------------------
@@ -342,7 +340,6 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
     mbar_init(&sm.jdiag_full, 1);
     mbar_init(&sm.thr_full, 2);
     mbar_init(&sm.thr_free, 4);
-    mbar_init(&sm.jblk_ready, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kIssuer0) {
@@ -528,16 +525,6 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
             }
           }
         }
-        if (kPrepassAhead && !(TC_DBG(P, 32))) {
-          // the "- J old" half of the in-block correction moves to the threshold side (see the epilogue)
-          mbar_wait(&sm.jblk_ready, (uint32_t)(gblk & 1));
-          const uint32_t w_old = sm.sbits[4 * p + (gblk & 3)][t];
-          for_each_site<0>([&](auto ic) {
-            constexpr int i = decltype(ic)::value;
-            const float old_i = ((w_old >> site_bit(i)) & 1u) ? 1.0f : 0.0f;
-            axpy_tail<i + 1>(v[0], sm.jblk[gblk & 1][i], old_i);
-          });
-        }
         if (gblk > 0) mbar_wait(&sm.thr_free, (uint32_t)((gblk - 1) & 1));  // the previous block's thresholds are in registers
 #pragma unroll
         for (int c = 0; c < kPer; ++c) {
@@ -574,7 +561,6 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
     stage_jblk(0, load_diag(0));
     uint4 jd = load_diag(1 % n_blocks);  // always one block ahead of the staged one
     named_bar_sync(1, kChains);
-    if (kPrepassAhead && !P.gemm_only) warp_arrive(&sm.jblk_ready);
     int gblk = 0;
     for (int gp = 0; gp < total_panels; ++gp) {
       const int p = gp % n_panels, buf = gp & 1;
@@ -592,12 +578,8 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
 #else
 #define TC_B(i) do {} while (0)
 #endif
-        // Thresholds of the block (threshold warps) -> registers.  The in-block correction is split as
-        // J (new - old) = J new - J old, and the "- J old" part of every earlier site of the block is moved to the
-        // other side of the comparison, thr'[i'] = thr[i'] + sum_{i<i'} J[i',i] old_i: nothing of it depends on the
-        // fields, so it is done ahead - by the threshold warps (M = 64, one chain per thread there) or here while
-        // the correction MMA of the previous block is in flight (M = 128).  The site-to-site dependency chain is
-        // then: compare -> 0/1 -> fma.
+        // Thresholds of the block (threshold warps) -> registers.  The site-to-site dependency chain of the update is:
+        // compare -> new - old -> packed fma into the fields of the sites still to come.
         float thr[kBlk];
         const uint32_t w_old = sm.sbits[blk][row];
         if (!P.gemm_only) {
@@ -605,13 +587,6 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
           thr_phase ^= 1u;
 #pragma unroll
           for (int i = 0; i < kBlk; ++i) thr[i] = sm.thr[i][row];
-          if (!kPrepassAhead) {
-            for_each_site<0>([&](auto ic) {
-              constexpr int i = decltype(ic)::value;
-              const float old_i = ((w_old >> site_bit(i)) & 1u) ? 1.0f : 0.0f;
-              axpy_tail<i + 1>(thr, sm.jblk[jb][i], old_i);
-            });
-          }
           warp_arrive(&sm.thr_free);
         }
         TC_B(26);
@@ -655,7 +630,8 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
             constexpr int i = decltype(ic)::value;
             if (P.fields_out && chain_ok) P.fields_out[(size_t)chain * N + i0 + i] = h[i];  // as compared (diagnostics)
             const bool up = h[i] > thr[i];
-            const float s_new = up ? 1.0f : 0.0f;
+            float s_new = up ? 1.0f : 0.0f;
+            s_new -= ((w_old >> site_bit(i)) & 1u) ? 1.0f : 0.0f;   // the correction carries new - old: -1, 0 or +1
             w_new |= up ? (1u << site_bit(i)) : 0u;
             // not yet visited sites of the block see the new value (rank-1 correction, branch free)
             if (!(TC_DBG(P, 8))) axpy_tail<i + 1>(h, sm.jblk[jb][i], s_new);
@@ -678,8 +654,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_tc_kernel(TcParams P, const
         }
         if (b == 3) warp_arrive(&sm.panel_done[gp & 3]);  // release: the producers may expand the chunk holding this panel
         named_bar_sync(1, kChains);  // the next block's jblk is complete, everybody is done with this block's
-        if (kPrepassAhead && !P.gemm_only) warp_arrive(&sm.jblk_ready);
-        if (warp == kEpilogue0) TC_ACC(12);
+            if (warp == kEpilogue0) TC_ACC(12);
       }  // release: the producers may expand the chunk holding this panel
     }
     if (!P.gemm_only && chain_ok) {  // unpack the final bits of this chain
