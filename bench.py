@@ -559,7 +559,7 @@ def run_b200_arm(args):
 
     # ---- end to end through the host API: pinned host lattices -> sweeps -> observables -----
     state_bytes = eng.state.numel() * 4
-    n_chunks = 16
+    n_chunks = 32   # upload / sweep pipeline granularity: the exposed ends are one chunk's upload and one chunk's sweeps
     chunk = max(1, n_rep // n_chunks)
     e2e = None
     try:
