@@ -242,6 +242,9 @@ class _PeerHalos:
     FLAG_WORDS = 16
 
     def __init__(self, drv: "SlabShardedIsing2D"):
+        """collective over drv.group.  Every phase that can fail locally is followed by an agreement (all-reduce of a
+        success flag), so that either every rank ends up with mapped neighbours or every rank raises - no rank is left
+        waiting in a collective for one that gave up."""
         import ctypes
 
         import torch
@@ -254,17 +257,31 @@ class _PeerHalos:
         self.lib = _lib.load()
         self.device = eng.state.device
         self.halo_words = 4 * drv.n_replicas * drv.wpr
+        self.base, self._opened, self.up, self.down = None, {}, None, None
+        self.msgs = [0, 0]
         nbytes = 4 * (self.halo_words + self.FLAG_WORDS)
-        with torch.cuda.device(self.device):
-            base = ctypes.c_void_p()
-            _lib.call("tsu_peer_alloc", ctypes.byref(base), nbytes)
-            self.base = base.value
-            handle = ctypes.create_string_buffer(64)
-            _lib.call("tsu_peer_get_handle", ctypes.c_void_p(self.base), handle)
+
+        def agree(ok: bool, what: str):
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=drv.group)
+            if int(flag.item()) == 0:
+                self._release()
+                raise RuntimeError(f"peer-mapped halo buffers are not available on every rank ({what})")
+
+        handle = ctypes.create_string_buffer(64)
+        ok = True
+        try:
+            with torch.cuda.device(self.device):
+                base = ctypes.c_void_p()
+                _lib.call("tsu_peer_alloc", ctypes.byref(base), nbytes)
+                self.base = base.value
+                _lib.call("tsu_peer_get_handle", ctypes.c_void_p(self.base), handle)
+        except Exception:
+            ok = False
+        agree(ok, "allocation / IPC export")
         mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=self.device)
         everyone = [torch.empty_like(mine) for _ in range(drv.world)]
         dist.all_gather(everyone, mine, group=drv.group)
-        self._opened = {}
 
         def open_rank(r):
             if r not in self._opened:
@@ -275,10 +292,34 @@ class _PeerHalos:
                 self._opened[r] = p.value
             return self._opened[r]
 
-        self.up = open_rank(drv.up) if drv.has_up else None
-        self.down = open_rank(drv.down) if drv.has_down else None
-        self.msgs = [0, 0]
-        dist.barrier(group=drv.group)  # every rank has mapped its neighbours before the first rows are written
+        try:
+            self.up = open_rank(drv.up) if drv.has_up else None
+            self.down = open_rank(drv.down) if drv.has_down else None
+        except Exception:
+            ok = False
+        agree(ok, "IPC import of a neighbour's buffer")  # doubles as the barrier before the first rows are written
+
+    def _release(self):
+        """local part of close(): unmap the neighbours, free the own buffer"""
+        import ctypes
+
+        import torch
+
+        from . import _lib
+
+        with torch.cuda.device(self.device):
+            for p in self._opened.values():
+                try:
+                    _lib.call("tsu_peer_close_handle", ctypes.c_void_p(p))
+                except Exception:
+                    pass
+            self._opened = {}
+            if self.base is not None:
+                try:
+                    _lib.call("tsu_peer_free", ctypes.c_void_p(self.base))
+                except Exception:
+                    pass
+                self.base = None
 
     def _flags(self, base):
         return None if base is None else base + 4 * self.halo_words
@@ -334,10 +375,9 @@ class _PeerHalos:
         with torch.cuda.device(self.device):
             for p in self._opened.values():
                 _lib.call("tsu_peer_close_handle", ctypes.c_void_p(p))
-            _dist().barrier(group=self.drv.group)
-            _lib.call("tsu_peer_free", ctypes.c_void_p(self.base))
-        self.base = None
-        self._opened = {}
+            self._opened = {}
+        _dist().barrier(group=self.drv.group)  # every mapping is closed before the owners free
+        self._release()
 
 
 class LatticeTempering:
