@@ -316,10 +316,19 @@ def trace_energy(energy_fn: Callable, dim: int, probe_points: Optional[np.ndarra
     if not isinstance(out, Sym):
         raise TraceError(f"the energy function returned {type(out).__name__} on symbolic inputs")
     if probe_points is not None:
+        checked = 0
         for p in np.atleast_2d(probe_points):
-            want = float(energy_fn(np.asarray(p, dtype=np.float64)))
-            got = tr.evaluate([out], p)[0]
+            try:
+                want = float(energy_fn(np.asarray(p, dtype=np.float64)))
+                got = tr.evaluate([out], p)[0]
+            except (ValueError, OverflowError, ZeroDivisionError, FloatingPointError):
+                continue  # outside the function's domain (log of a negative number, ...): nothing to compare here
+            if not (math.isfinite(want) and math.isfinite(got)):
+                continue
             if not (abs(got - want) <= rtol * max(1.0, abs(want))):
                 raise TraceError(f"the traced expression gives {got!r} where the function gives {want!r}")
+            checked += 1
+        if checked == 0:
+            raise TraceError("the energy function is not finite at any of the probe points around x_init")
     grads = tr.gradient(out)
     return tr, out, grads
