@@ -376,3 +376,59 @@ def test_two_word_threads_equal_four_word_threads(tuning, monkeypatch):
         assert want._jit == 0
         j2.init_random().sweep(4)
         assert torch.equal(j2.state, want.state)
+
+
+@pytest.mark.parametrize("rows,cols,periodic_cols,split", [(1200, 1024, True, 4), (1100, 1000, False, 3), (2100, 512, True, 8),
+                                                          (700, 1024, True, 2), (64, 256, True, 0)])
+def test_slab_driver_without_neighbours_equals_open_rows(rows, cols, periodic_cols, split, tuning):
+    """tsu_ising2d_slab_sweeps_p2p with no rank above or below: interior row ranges on streams of their own, boundary
+    rows on the side stream - the bits of the plain sweep of a lattice with open rows"""
+    import ctypes
+
+    import torch
+
+    from tsu_emulator_b200 import _lib
+    tuning.setenv("TSU_LATTICE_RESIDENT", "0")
+    if split:
+        tuning.setenv("TSU_LATTICE_SPLIT", str(split))
+    kw = dict(n_replicas=2, temperature=2.269, periodic=periodic_cols, seed=23, field=0.02)
+    ref = make_engine(rows, cols, **kw)
+    ref.wrap_rows = False
+    ref.init_random().sweep(5)
+    eng = make_engine(rows, cols, **kw)
+    eng.wrap_rows = False
+    eng.init_random()
+    wpr = eng.state.shape[-1]
+    halo = torch.zeros(4 * 2 * wpr + 16, dtype=torch.int32, device="cuda")
+    flags = halo[4 * 2 * wpr:]
+    side = torch.cuda.Stream()
+    for n in (2, 3):
+        _lib.call("tsu_ising2d_slab_sweeps_p2p", 0, _lib.ptr(eng.state), 2, rows, cols, int(eng.wrap_cols), _lib.ptr(eng.lut),
+                  None, eng.seed, eng.sweep_index, n, 0, 0, _lib.ptr(halo), _lib.ptr(flags), None, None, None, None, 0, 0,
+                  int(torch.cuda.current_stream().cuda_stream), int(side.cuda_stream))
+        eng.sweep_index += n
+    torch.cuda.synchronize()
+    assert torch.equal(eng.state, ref.state)
+    assert int(flags[8]) == 0
+
+
+@pytest.mark.parametrize("rows,cols,periodic,split", [(2048, 1024, True, 8), (1500, 1000, False, 5), (1024, 512, True, 3),
+                                                     (1030, 1026, True, 4)])
+def test_row_ranges_on_their_own_streams_equal_one_launch(rows, cols, periodic, split, tuning):
+    """TSU_LATTICE_SPLIT: the half-sweeps of tsu_ising2d_sweeps cut into row ranges that only wait for their neighbours
+    (what large single lattices do by default) - same bits as one launch per half-sweep, periodic rows included"""
+    import torch
+    tuning.setenv("TSU_LATTICE_RESIDENT", "0")
+    tuning.setenv("TSU_LATTICE_SPLIT", "1")
+    kw = dict(n_replicas=2, temperature=2.269, periodic=periodic, seed=29, field=-0.03)
+    ref = make_engine(rows, cols, **kw).init_random().sweep(2).sweep(3)
+    tuning.setenv("TSU_LATTICE_SPLIT", str(split))
+    got = make_engine(rows, cols, **kw).init_random().sweep(2).sweep(3)
+    assert torch.equal(got.state, ref.state)
+    side = torch.cuda.Stream()      # and from a stream that is not the default one
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        got.sweep(2)
+    ref.sweep(2)
+    torch.cuda.synchronize()
+    assert torch.equal(got.state, ref.state)

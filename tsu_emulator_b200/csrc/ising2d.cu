@@ -204,9 +204,33 @@ __device__ __forceinline__ uint32_t update_word(uint32_t a, uint32_t b, uint32_t
   return lt;
 }
 
+#ifdef TSU_LATTICE_TRACE  // diagnosis build (tools/lattice_trace.py): when and where every CTA of the last launches ran
+constexpr int kTraceCtas = 8192;
+__device__ unsigned long long g_lat_trace[4][3 * kTraceCtas];  // [launch & 3][cta] = start ns, end ns, SM id
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
+
 template <int W, int MINB>
 __global__ void __launch_bounds__(128, MINB) half_sweep_fast_kernel(SweepParams P) {
+#ifdef TSU_LATTICE_TRACE
+  const unsigned long long t_start = trace_now();
+#endif
   tsu_fast::half_sweep_fast_body<W>(P);
+#ifdef TSU_LATTICE_TRACE
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x < kTraceCtas) {
+    unsigned smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned long long* t = g_lat_trace[(P.sweep * 2 + P.colour) & 3] + 3 * blockIdx.x;
+    t[0] = t_start;
+    t[1] = trace_now();
+    t[2] = smid;
+  }
+#endif
 }
 
 // One word of (replica rep, colour, local row i): any size, open or periodic edges, ragged last word.
@@ -555,6 +579,20 @@ __global__ void slab_wait_kernel(const uint32_t* flag_a, const uint32_t* flag_b,
   }
 }
 
+// streams the slab driver launches its extra interior row ranges on: created once per device, never destroyed
+std::mutex g_slab_stream_mutex;
+std::map<int, std::vector<cudaStream_t>> g_slab_streams;
+cudaStream_t slab_stream(int dev, int idx) {
+  std::lock_guard<std::mutex> lock(g_slab_stream_mutex);
+  std::vector<cudaStream_t>& v = g_slab_streams[dev];
+  while ((int)v.size() <= idx) {
+    cudaStream_t s = nullptr;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    v.push_back(s);
+  }
+  return v[idx];
+}
+
 bool geom_ok(int n_replicas, int rows, int cols) {
   // counter word 1 of the lattice stream keeps the global row in 24 bits, counter word 0 the 4-word group in 24
   return n_replicas > 0 && rows > 0 && cols > 0 && cols < (1 << 26) && rows <= TSU_LATTICE_MAX_ROWS;
@@ -563,13 +601,15 @@ bool geom_ok(int n_replicas, int rows, int cols) {
 bool rows_ok(int rows, int row0) { return row0 >= 0 && (long long)row0 + rows <= TSU_LATTICE_MAX_ROWS; }
 
 // Tuning knobs (never change results), read once per process:
-//   TSU_LATTICE_STRIP  rows per thread strip of the wide kernel (default: 64, shortened until the grid fills the GPU)
+//   TSU_LATTICE_STRIP  rows per thread strip of the wide kernel (default: 128, shortened until the grid fills the GPU)
+//   TSU_LATTICE_SPLIT  row ranges a half-sweep is cut into (split_ranges(); 1 = one launch per half-sweep)
 //   TSU_LATTICE_W      words per thread of the prebuilt wide kernel (2 or 4)
 //   TSU_LATTICE_OPEN_GENERIC / TSU_LATTICE_OBS_GENERIC / TSU_LATTICE_RESIDENT=0  force the one-thread-per-word kernels
+//   TSU_JIT_THREADS (32 / 64 / 128 threads per CTA),
 //   TSU_JIT_W, TSU_JIT_MINB, TSU_JIT_UNROLL   words per thread, CTAs per SM and row-loop unrolling the run-time
 //                                             specialised kernel is compiled for
 struct Tuning {
-  int strip = 0, w = 0, open_generic = 0, obs_generic = 0, resident = 1, jit_w = 0, jit_minb = 0, jit_unroll = 0;
+  int strip = 0, w = 0, open_generic = 0, obs_generic = 0, resident = 1, jit_w = 0, jit_minb = 0, jit_unroll = 0, jit_threads = 0, split = -1;
   Tuning() {
     auto num = [](const char* name, int dflt) {
       const char* e = getenv(name);
@@ -583,11 +623,14 @@ struct Tuning {
     jit_w = num("TSU_JIT_W", 0);
     jit_minb = num("TSU_JIT_MINB", 0);
     jit_unroll = num("TSU_JIT_UNROLL", 0);
+    jit_threads = num("TSU_JIT_THREADS", 0);
+    split = num("TSU_LATTICE_SPLIT", -1);
   }
 };
 Tuning g_tuning;  // read when the library is loaded; tsu_ising2d_reload_tuning() reads the environment again
 const Tuning& tuning() { return g_tuning; }
-constexpr int kDefaultW = 4, kDefaultJitW = 4, kDefaultJitMinB = 5;  // 5 CTAs/SM (93 registers): +1 % over 4, measured
+constexpr int kDefaultW = 4, kDefaultJitW = 4, kDefaultJitMinB = 5, kDefaultJitThreads = 128;
+constexpr int kDefaultSplit = 8, kMaxSplit = 8;  // row ranges of one half-sweep launched on streams of their own  // 5 CTAs/SM (93 registers): +1 % over 4, measured
 
 Geom make_geom(int n_replicas, int rows, int cols, int wrap_rows, int wrap_cols, int row0) {
   Geom g;
@@ -611,20 +654,23 @@ std::mutex g_jit_mutex;
 std::map<std::string, int> g_jit_cache;  // "device:t0,..,t7" -> handle
 struct JitKernel {
   void* fn;
-  int w;  // words per thread it was compiled for
+  int w;        // words per thread it was compiled for
+  int threads;  // threads per CTA it was compiled for
 };
 std::vector<JitKernel> g_jit_functions;  // handle - 1 -> kernel
 
 JitKernel jit_function(int handle) {
   std::lock_guard<std::mutex> lock(g_jit_mutex);
-  if (handle < 1 || handle > (int)g_jit_functions.size()) return JitKernel{nullptr, 0};
+  if (handle < 1 || handle > (int)g_jit_functions.size()) return JitKernel{nullptr, 0, 0};
   return g_jit_functions[handle - 1];
 }
 
 int launch_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows, int wrap_cols, int colour,
                       const uint32_t* d_lut, const int32_t* d_lut_index, uint64_t seed, uint32_t sweep,
                       uint32_t replica0, int row0, const uint32_t* d_halo_top, const uint32_t* d_halo_bot,
-                      cudaStream_t st, JitKernel jit = JitKernel{nullptr, 0}, int upd_begin = 0, int upd_end = -1) {
+                      cudaStream_t st, JitKernel jit = JitKernel{nullptr, 0, 0}, int upd_begin = 0, int upd_end = -1,
+                      int pieces = 1) {
+  // pieces: this launch is one of `pieces` row ranges of a half-sweep that run concurrently (split_ranges())
   if (upd_end < 0) upd_end = rows;  // local rows [upd_begin, upd_end) are updated (default: all)
   if (upd_begin >= upd_end) return TSU_OK;
   SweepParams P;
@@ -664,7 +710,10 @@ int launch_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int
     // strips long enough to amortise the two halo rows and the warp prologue, short enough to fill 148 SMs x 16 warps
     const long long target_threads = 148LL * 2048;
     int strip = 128;
-    while (strip > 1 && (long long)n_replicas * nvec * ((frows + strip - 1) / strip) < target_threads) strip >>= 1;
+    const long long srows = (long long)frows * pieces;
+    while (strip > 1 && (long long)n_replicas * nvec * ((srows + strip - 1) / strip) < target_threads) strip >>= 1;
+    // the tail of one range is filled by the next: longer strips (less set-up per row) cost nothing there
+    if (pieces >= 4) strip = strip * 4 < 128 ? strip * 4 : 128;
     if (tuning().strip > 0) strip = tuning().strip;
     P.strip_rows = strip;
     P.n_strips = (frows + strip - 1) / strip;
@@ -675,7 +724,7 @@ int launch_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int
     const unsigned grid = blocks_for(total, 128);
     if (use_jit) {  // table-specialised build of the same kernel body
       void* args[] = {&P};
-      if (tsu_jit::launch(jit.fn, grid, 128, 0, (void*)st, args) != 0) return 999;  // driver-API launch failure
+      if (tsu_jit::launch(jit.fn, blocks_for(total, jit.threads), jit.threads, 0, (void*)st, args) != 0) return 999;  // driver-API launch failure
     } else if (W == 2) {
       half_sweep_fast_kernel<2, 8><<<grid, 128, 0, st>>>(P);
     } else {
@@ -700,6 +749,80 @@ int launch_half_sweep(uint32_t* d_state, int n_replicas, int rows, int cols, int
     const long long total = (long long)n_replicas * (upd_end - upd_begin) * P.g.wpr;
     half_sweep_generic_kernel<<<blocks_for(total, 128), 128, 0, st>>>(P);
   }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? TSU_OK : (int)e;
+}
+
+// Row ranges a half-sweep is cut into.  One launch per half-sweep loses ~15 us to its tail (launch gap, the last warps
+// finishing alone: measured, tools/lattice_trace.py); ranges on streams of their own, each depending only on its
+// neighbours' previous half-sweep, let the next half-sweep start while this one drains.  Pays between ~0.1 and ~5 ms
+// per half-sweep (6.8 % on a 16384 x 131072 slab, 2.5 % on 131072^2); TSU_LATTICE_SPLIT overrides (1 = never).
+int split_ranges(int n_replicas, int rows, int cols) {
+  int K;
+  if (tuning().split >= 1) {
+    K = tuning().split < kMaxSplit ? tuning().split : kMaxSplit;
+  } else {
+    const double sites = (double)n_replicas * rows * cols;
+    K = (sites >= 1e9 && sites <= 6e10) ? kDefaultSplit : 1;
+  }
+  while (K > 1 && rows / K < 256) --K;  // short ranges would only add launches
+  return K;
+}
+
+// the whole-lattice sweeps of tsu_ising2d_sweeps / _sweeps_jit (no halos)
+int launch_sweeps(uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows, int wrap_cols, const uint32_t* d_lut,
+                  const int32_t* d_lut_index, uint64_t seed, uint32_t sweep0, int n_sweeps, uint32_t replica0,
+                  cudaStream_t st, JitKernel jit) {
+  const int K = split_ranges(n_replicas, rows, cols);
+  if (K <= 2 || n_sweeps == 0) {
+    for (int t = 0; t < 2 * n_sweeps; ++t) {
+      int rc = launch_half_sweep(d_state, n_replicas, rows, cols, wrap_rows, wrap_cols, t & 1, d_lut, d_lut_index, seed,
+                                 sweep0 + (uint32_t)(t >> 1), replica0, 0, nullptr, nullptr, st, jit);
+      if (rc != TSU_OK) return rc;
+    }
+    return TSU_OK;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaStream_t sub[kMaxSplit];
+  sub[0] = st;
+  for (int k = 1; k < K; ++k) {
+    sub[k] = slab_stream(dev, k - 1);
+    if (!sub[k]) return (int)cudaGetLastError();
+  }
+  int bound[kMaxSplit + 1];
+  for (int k = 0; k <= K; ++k) bound[k] = (int)((long long)rows * k / K);
+  cudaEvent_t ev[kMaxSplit][2], ev_join;
+  bool ev_ok = cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) == cudaSuccess;
+  for (int k = 0; k < K && ev_ok; ++k)
+    for (int j = 0; j < 2 && ev_ok; ++j) ev_ok = cudaEventCreateWithFlags(&ev[k][j], cudaEventDisableTiming) == cudaSuccess;
+  if (!ev_ok) return (int)cudaGetLastError();
+  cudaEventRecord(ev_join, st);
+  for (int k = 1; k < K; ++k) cudaStreamWaitEvent(sub[k], ev_join, 0);
+  int rc = TSU_OK;
+  for (int t = 0; t < 2 * n_sweeps && rc == TSU_OK; ++t) {
+    const int j = t & 1, jp = j ^ 1;
+    // the range launched first changes every half-sweep: with periodic rows range 0 depends on range K - 1, and what
+    // the first range of a half-sweep depends on should be what the half-sweep before launched first
+    for (int i = 0; i < K && rc == TSU_OK; ++i) {
+      const int k = (t + i) % K, above = (k + K - 1) % K, below = (k + 1) % K;
+      if (t > 0) {
+        if (k > 0 || wrap_rows) cudaStreamWaitEvent(sub[k], ev[above][jp], 0);
+        if (k + 1 < K || wrap_rows) cudaStreamWaitEvent(sub[k], ev[below][jp], 0);
+      }
+      rc = launch_half_sweep(d_state, n_replicas, rows, cols, wrap_rows, wrap_cols, t & 1, d_lut, d_lut_index, seed,
+                             sweep0 + (uint32_t)(t >> 1), replica0, 0, nullptr, nullptr, sub[k], jit, bound[k], bound[k + 1], K);
+      cudaEventRecord(ev[k][j], sub[k]);
+    }
+  }
+  for (int k = 1; k < K; ++k) {  // the caller's stream continues after everything issued here
+    cudaEventRecord(ev_join, sub[k]);
+    cudaStreamWaitEvent(st, ev_join, 0);
+  }
+  for (int k = 0; k < K; ++k)
+    for (int j = 0; j < 2; ++j) cudaEventDestroy(ev[k][j]);
+  cudaEventDestroy(ev_join);
+  if (rc != TSU_OK) return rc;
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? TSU_OK : (int)e;
 }
@@ -736,6 +859,12 @@ int launch_resident_sweeps(uint32_t* d_state, int n_replicas, int rows, int cols
 extern "C" {
 
 void tsu_ising2d_reload_tuning(void) { g_tuning = Tuning(); }
+
+#ifdef TSU_LATTICE_TRACE
+int tsu_debug_lattice_trace(unsigned long long* h_out) {  // 4 x 3 x 8192 words
+  return (int)cudaMemcpyFromSymbol(h_out, g_lat_trace, sizeof(unsigned long long) * 4 * 3 * kTraceCtas);
+}
+#endif
 
 int64_t tsu_ising2d_words_per_row(int cols) { return cols > 0 ? words_per_row(cols) : 0; }
 
@@ -791,7 +920,7 @@ int tsu_ising2d_half_sweep_rows(int jit_handle, uint32_t* d_state, int n_replica
   TSU_CHECK_ARG(!wrap_cols || (cols % 2 == 0 && cols > 2));
   TSU_CHECK_ARG(!wrap_rows || (rows % 2 == 0 && rows > 2) || d_halo_top || d_halo_bot);
   TSU_CHECK_ARG(row_begin >= 0 && row_begin <= row_end && row_end <= rows);
-  const JitKernel jit = (jit_handle > 0 && !d_lut_index) ? jit_function(jit_handle) : JitKernel{nullptr, 0};
+  const JitKernel jit = (jit_handle > 0 && !d_lut_index) ? jit_function(jit_handle) : JitKernel{nullptr, 0, 0};
   return launch_half_sweep(d_state, n_replicas, rows, cols, wrap_rows, wrap_cols, colour, d_lut, d_lut_index, seed, sweep,
                            replica0, row0, d_halo_top, d_halo_bot, tsu_stream(stream), jit, row_begin, row_end);
 }
@@ -806,20 +935,36 @@ int tsu_ising2d_slab_sweeps_p2p(int jit_handle, uint32_t* d_state, int n_replica
   TSU_CHECK_ARG(rows >= 4 && n_sweeps >= 0 && main_stream != side_stream);
   TSU_CHECK_ARG(!wrap_cols || (cols % 2 == 0 && cols > 2));
   TSU_CHECK_ARG((d_up_halo == nullptr) == (d_up_flags == nullptr) && (d_down_halo == nullptr) == (d_down_flags == nullptr));
-  const JitKernel jit = (jit_handle > 0 && !d_lut_index) ? jit_function(jit_handle) : JitKernel{nullptr, 0};
+  const JitKernel jit = (jit_handle > 0 && !d_lut_index) ? jit_function(jit_handle) : JitKernel{nullptr, 0, 0};
   cudaStream_t main = tsu_stream(main_stream), side = tsu_stream(side_stream);
   const int wpr = words_per_row(cols);
   const size_t side_words = (size_t)n_replicas * wpr;  // one halo row set
   auto halo = [&](uint32_t* base, int colour, int which) { return base ? base + ((size_t)colour * 2 + which) * side_words : nullptr; };
   auto flag = [&](uint32_t* base, int colour, int which) { return base ? base + colour * 2 + which : nullptr; };
   uint32_t msgs[2] = {msgs_colour0, msgs_colour1};
-  cudaEvent_t ev_int[2], ev_bnd[2], ev_join;
-  for (int k = 0; k < 2; ++k) {
-    if (cudaEventCreateWithFlags(&ev_int[k], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ev_bnd[k], cudaEventDisableTiming) != cudaSuccess)
-      return (int)cudaGetLastError();
+  // The interior rows are cut into row ranges launched on streams of their own: range k of a half-sweep depends only on
+  // ranges k - 1, k, k + 1 (and, at the ends, on the boundary rows) of the half-sweep before, so the first ranges of
+  // the next half-sweep fill the SMs while the last ranges of this one drain.  A single launch per half-sweep loses
+  // ~15 us to its tail (launch gap + the last warps finishing alone), 6 % of a 16384 x 131072 slab.
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int K = split_ranges(n_replicas, rows - 2, cols);
+  cudaStream_t sub[kMaxSplit];
+  sub[0] = main;
+  for (int k = 1; k < K; ++k) {
+    sub[k] = slab_stream(dev, k - 1);
+    if (!sub[k]) return (int)cudaGetLastError();
   }
-  if (cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) return (int)cudaGetLastError();
+  int bound[kMaxSplit + 1];  // range k = local rows [bound[k], bound[k + 1])
+  for (int k = 0; k <= K; ++k) bound[k] = 1 + (int)((long long)(rows - 2) * k / K);
+  // strips as long as one launch over the whole interior would use
+  cudaEvent_t ev_sub[kMaxSplit][2], ev_bnd[2], ev_join;
+  bool ev_ok = cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) == cudaSuccess;
+  for (int j = 0; j < 2 && ev_ok; ++j) {
+    ev_ok = cudaEventCreateWithFlags(&ev_bnd[j], cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; k < K && ev_ok; ++k) ev_ok = cudaEventCreateWithFlags(&ev_sub[k][j], cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ev_ok) return (int)cudaGetLastError();
   const unsigned send_grid = blocks_for(2LL * n_replicas * (wpr / 4), 256) < 64u ? blocks_for(2LL * n_replicas * (wpr / 4), 256) : 64u;
   // what a half-sweep of `colour` sends afterwards: my first row to the rank above (its "below" halo), my last row
   // to the rank below (its "above" halo), then the message number
@@ -830,23 +975,32 @@ int tsu_ising2d_slab_sweeps_p2p(int jit_handle, uint32_t* d_state, int n_replica
     slab_signal_kernel<<<1, 1, 0, side>>>(flag(d_up_flags, colour, 1), flag(d_down_flags, colour, 0), msgs[colour]);
   };
   int rc = TSU_OK;
-  // everything the caller queued on the main stream (e.g. a changed state) precedes the first rows sent
+  // everything the caller queued on the main stream (e.g. a changed state) precedes the first rows sent and updated
   cudaEventRecord(ev_join, main);
   cudaStreamWaitEvent(side, ev_join, 0);
+  for (int k = 1; k < K; ++k) cudaStreamWaitEvent(sub[k], ev_join, 0);
   send(1);  // colour 0 goes first and reads colour 1
-  bool have_int = false, have_bnd = false;
   for (int t = 0; t < 2 * n_sweeps && rc == TSU_OK; ++t) {
-    const int colour = t & 1, opp = 1 - colour, k = t & 1;
+    const int colour = t & 1, opp = 1 - colour, j = t & 1, jp = j ^ 1;
     const uint32_t sweep = sweep0 + (uint32_t)(t >> 1);
-    // interior rows on the main stream: they read and overwrite rows next to the boundary rows of the previous half-sweep
-    if (have_bnd) cudaStreamWaitEvent(main, ev_bnd[k ^ 1], 0);
-    rc = launch_half_sweep(d_state, n_replicas, rows, cols, 0, wrap_cols, colour, d_lut, d_lut_index, seed, sweep, replica0,
-                           row0, nullptr, nullptr, main, jit, 1, rows - 1);
+    // interior ranges: each reads and overwrites rows next to what its neighbours updated in the half-sweep before
+    for (int k = 0; k < K && rc == TSU_OK; ++k) {
+      if (t > 0) {
+        if (k > 0) cudaStreamWaitEvent(sub[k], ev_sub[k - 1][jp], 0);
+        if (k + 1 < K) cudaStreamWaitEvent(sub[k], ev_sub[k + 1][jp], 0);
+        if (k == 0 || k + 1 == K) cudaStreamWaitEvent(sub[k], ev_bnd[jp], 0);
+      }
+      rc = launch_half_sweep(d_state, n_replicas, rows, cols, 0, wrap_cols, colour, d_lut, d_lut_index, seed, sweep, replica0,
+                             row0, nullptr, nullptr, sub[k], jit, bound[k], bound[k + 1], K);
+      cudaEventRecord(ev_sub[k][j], sub[k]);
+    }
     if (rc != TSU_OK) break;
-    // boundary rows on the side stream: after the previous interior update and the neighbours' rows of the other colour
-    if (have_int) cudaStreamWaitEvent(side, ev_int[k ^ 1], 0);
-    cudaEventRecord(ev_int[k], main);
-    have_int = true;
+    // boundary rows on the side stream: after the previous update of the rows next to them and the arrival of the
+    // neighbours' rows of the other colour
+    if (t > 0) {
+      cudaStreamWaitEvent(side, ev_sub[0][jp], 0);
+      if (K > 1) cudaStreamWaitEvent(side, ev_sub[K - 1][jp], 0);
+    }
     const uint32_t* top = d_up_halo ? halo(d_halo, opp, 0) : nullptr;
     const uint32_t* bot = d_down_halo ? halo(d_halo, opp, 1) : nullptr;
     if (top || bot)
@@ -857,15 +1011,19 @@ int tsu_ising2d_slab_sweeps_p2p(int jit_handle, uint32_t* d_state, int n_replica
     if (rc == TSU_OK)
       rc = launch_half_sweep(d_state, n_replicas, rows, cols, 0, wrap_cols, colour, d_lut, d_lut_index, seed, sweep, replica0,
                              row0, top, bot, side, jit, rows - 1, rows);
-    cudaEventRecord(ev_bnd[k], side);
-    have_bnd = true;
+    cudaEventRecord(ev_bnd[j], side);
     send(colour);
   }
+  // the caller's stream continues after everything issued here
   cudaEventRecord(ev_join, side);
   cudaStreamWaitEvent(main, ev_join, 0);
-  for (int k = 0; k < 2; ++k) {
-    cudaEventDestroy(ev_int[k]);
-    cudaEventDestroy(ev_bnd[k]);
+  for (int k = 1; k < K; ++k) {
+    cudaEventRecord(ev_join, sub[k]);
+    cudaStreamWaitEvent(main, ev_join, 0);
+  }
+  for (int j = 0; j < 2; ++j) {
+    cudaEventDestroy(ev_bnd[j]);
+    for (int k = 0; k < K; ++k) cudaEventDestroy(ev_sub[k][j]);
   }
   cudaEventDestroy(ev_join);
   if (rc != TSU_OK) return rc;
@@ -882,14 +1040,8 @@ int tsu_ising2d_sweeps(uint32_t* d_state, int n_replicas, int rows, int cols, in
   if (n_sweeps > 0 && resident_eligible(n_replicas, rows, cols))
     return launch_resident_sweeps(d_state, n_replicas, rows, cols, wrap_rows, wrap_cols, d_lut, d_lut_index, seed, sweep0,
                                   n_sweeps, replica0, tsu_stream(stream));
-  for (int t = 0; t < n_sweeps; ++t) {
-    for (int colour = 0; colour < 2; ++colour) {
-      int rc = launch_half_sweep(d_state, n_replicas, rows, cols, wrap_rows, wrap_cols, colour, d_lut, d_lut_index,
-                                 seed, sweep0 + (uint32_t)t, replica0, 0, nullptr, nullptr, tsu_stream(stream));
-      if (rc != TSU_OK) return rc;
-    }
-  }
-  return TSU_OK;
+  return launch_sweeps(d_state, n_replicas, rows, cols, wrap_rows, wrap_cols, d_lut, d_lut_index, seed, sweep0, n_sweeps,
+                       replica0, tsu_stream(stream), JitKernel{nullptr, 0, 0});
 }
 
 int tsu_ising2d_half_sweep_injected(uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows,
@@ -982,14 +1134,17 @@ int tsu_ising2d_jit_prepare(const uint32_t* h_lut, const char* src_dir, char* lo
   for (int k = 0; k < 8; ++k) src += "#define TSU_FT" + std::to_string(k) + " " + std::to_string(tab[k]) + "\n";
   src += "#define TSU_FZ " + std::to_string(fz) + "\n";
   const int jw = tuning().jit_w == 2 ? 2 : (tuning().jit_w == 4 ? 4 : kDefaultJitW);
-  const int minb = tuning().jit_minb > 0 ? tuning().jit_minb : (jw == 2 ? 8 : kDefaultJitMinB);
+  const int jt = (tuning().jit_threads == 32 || tuning().jit_threads == 64) ? tuning().jit_threads : kDefaultJitThreads;
+  const int minb = tuning().jit_minb > 0 ? tuning().jit_minb : (jw == 2 ? 8 : kDefaultJitMinB) * (128 / jt);
   src += "#define TSU_ALWAYS " + std::to_string((h_lut[25] >> 20) & 31u) + "u\n";
   src += "#define TSU_JIT_MINB " + std::to_string(minb) + "\n";
   src += "#define TSU_JIT_W " + std::to_string(jw) + "\n";
+  src += "#define TSU_JIT_THREADS " + std::to_string(jt) + "\n";
+  src += "#define TSU_FAST_WARPS " + std::to_string(jt / 32) + "\n";
   if (tuning().jit_unroll > 1) src += "#define TSU_ROW_UNROLL " + std::to_string(tuning().jit_unroll) + "\n";
   src +=
       "#include \"ising2d_fast.cuh\"\n"
-      "extern \"C\" __global__ void __launch_bounds__(128, TSU_JIT_MINB) tsu_jit_half_sweep(tsu_fast::SweepParams P) {\n"
+      "extern \"C\" __global__ void __launch_bounds__(TSU_JIT_THREADS, TSU_JIT_MINB) tsu_jit_half_sweep(tsu_fast::SweepParams P) {\n"
       "  tsu_fast::half_sweep_fast_body<TSU_JIT_W>(P);\n}\n";
   std::string log;
   void* fn = tsu_jit::compile(src, "tsu_jit.cu", "tsu_jit_half_sweep", src_dir, log);
@@ -998,7 +1153,7 @@ int tsu_ising2d_jit_prepare(const uint32_t* h_lut, const char* src_dir, char* lo
     g_jit_cache[key] = 0;
     return 0;
   }
-  g_jit_functions.push_back(JitKernel{fn, jw});
+  g_jit_functions.push_back(JitKernel{fn, jw, jt});
   const int handle = (int)g_jit_functions.size();
   g_jit_cache[key] = handle;
   return handle;
@@ -1025,15 +1180,8 @@ int tsu_ising2d_sweeps_jit(int jit_handle, uint32_t* d_state, int n_replicas, in
   if (n_sweeps > 0 && resident_eligible(n_replicas, rows, cols))  // launch latency dominates: one launch for everything
     return launch_resident_sweeps(d_state, n_replicas, rows, cols, wrap_rows, wrap_cols, d_lut, nullptr, seed, sweep0,
                                   n_sweeps, replica0, tsu_stream(stream));
-  const JitKernel fn = jit_function(jit_handle);
-  for (int t = 0; t < n_sweeps; ++t) {
-    for (int colour = 0; colour < 2; ++colour) {
-      int rc = launch_half_sweep(d_state, n_replicas, rows, cols, wrap_rows, wrap_cols, colour, d_lut, nullptr, seed,
-                                 sweep0 + (uint32_t)t, replica0, 0, nullptr, nullptr, tsu_stream(stream), fn);
-      if (rc != TSU_OK) return rc;
-    }
-  }
-  return TSU_OK;
+  return launch_sweeps(d_state, n_replicas, rows, cols, wrap_rows, wrap_cols, d_lut, nullptr, seed, sweep0, n_sweeps, replica0,
+                       tsu_stream(stream), jit_function(jit_handle));
 }
 
 }  // extern "C"

@@ -219,10 +219,13 @@ __device__ __forceinline__ uint32_t drain_pass(uint32_t* ring, uint32_t head, ui
 // Periodic columns at a word boundary, every word full, a neighbour row above and below every local row in
 // [row_begin, row_end) (wrap or halo).  Threads of a warp always belong to the same replica (thread index space
 // padded to a multiple of 32 per replica), so the threshold tables are warp-uniform.
+#ifndef TSU_FAST_WARPS
+#define TSU_FAST_WARPS 4  // warps per CTA the kernel is launched with (warps never cooperate: any CTA size works)
+#endif
 template <int W>
 __device__ __forceinline__ void half_sweep_fast_body(const SweepParams& P) {
   constexpr int REC = TieRec<W>::kWords;
-  __shared__ __align__(16) uint32_t tie_rings[4][kRingSlots * REC];
+  __shared__ __align__(16) uint32_t tie_rings[TSU_FAST_WARPS][kRingSlots * REC];  // one ring per warp of the CTA
   const Geom& g = P.g;
   const int nvec = P.nvec_fast * (4 / W);  // W-word groups per row
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
