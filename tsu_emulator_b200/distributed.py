@@ -163,6 +163,9 @@ class SlabShardedIsing2D:
         if self._p2p is not None:
             self._p2p.sweeps(int(n_sweeps))
             return self
+        if self.world == 1 and getattr(self.engine, "is_slab", True) is False and hasattr(self.engine, "sweep"):
+            self.engine.sweep(int(n_sweeps))  # the one slab is the whole lattice: no halos, the engine's own sweeps
+            return self
         if not self.overlap:
             for _ in range(n_sweeps):
                 self.half_sweep(0)
