@@ -125,7 +125,9 @@ int tsu_ising2d_half_sweep_rows(int jit_handle, uint32_t* d_state, int n_replica
  * d_up_* / d_down_* are the mapped buffers of the ranks holding the rows above / below (NULL = open edge).
  * msgs_colour0/1: messages already exchanged per colour before this call (every rank passes the same numbers; the
  * call exchanges n_sweeps of colour 0 and n_sweeps + 1 of colour 1).  rows >= 4.  Bits are identical to the
- * unsharded lattice (global-row Philox counters). */
+ * unsharded lattice (global-row Philox counters).  Large slabs: the interior rows of a half-sweep are launched as up
+ * to 8 row ranges on library-owned streams (see tsu_ising2d_sweeps); everything is joined back into main_stream
+ * before the call returns. */
 int tsu_ising2d_slab_sweeps_p2p(int jit_handle, uint32_t* d_state, int n_replicas, int rows, int cols,
                                 int wrap_cols, const uint32_t* d_lut, const int32_t* d_lut_index,
                                 uint64_t seed, uint32_t sweep0, int n_sweeps, uint32_t replica0, int row0,
@@ -136,7 +138,12 @@ int tsu_ising2d_slab_sweeps_p2p(int jit_handle, uint32_t* d_state, int n_replica
 /* n_sweeps full sweeps (black then white), sweep indices sweep0 .. sweep0+n_sweeps-1, no halos.
  * Two launches per sweep; lattices of at most 4096 words per replica in batches that would not fill the GPU
  * (BASELINE config 1: 50 x 50) run ALL sweeps of the call in ONE launch, one thread block per replica.  Same
- * bits either way (TSU_LATTICE_RESIDENT=0 disables the single-launch form). */
+ * bits either way (TSU_LATTICE_RESIDENT=0 disables the single-launch form).
+ * Launches of 1e9 .. 6e10 sites with at least 2048 rows: every half-sweep is cut into 8 row ranges launched on
+ * library-owned non-blocking streams (created once per device), range k waiting by events only for ranges k-1, k,
+ * k+1 of the half-sweep before, so that the next half-sweep fills the SMs while this one drains (+3 .. 11 %).  The
+ * extra streams fork from `stream` and are joined back into it before the call returns: to the caller the call is
+ * still ordered on `stream` alone.  TSU_LATTICE_SPLIT=1 keeps one launch per half-sweep; same bits either way. */
 int tsu_ising2d_sweeps(uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows,
                        int wrap_cols, const uint32_t* d_lut, const int32_t* d_lut_index,
                        uint64_t seed, uint32_t sweep0, int n_sweeps, uint32_t replica0,
