@@ -432,3 +432,20 @@ def test_row_ranges_on_their_own_streams_equal_one_launch(rows, cols, periodic, 
     ref.sweep(2)
     torch.cuda.synchronize()
     assert torch.equal(got.state, ref.state)
+
+
+@pytest.mark.parametrize("periodic,per_replica_T", [(True, False), (False, True), (True, True)])
+def test_replica_chunks_on_their_own_streams_equal_one_launch(periodic, per_replica_T, tuning):
+    """batches of lattices: chunks of replicas on streams of their own (TSU_LATTICE_SPLIT > 1 forces it on a small
+    batch), per-replica threshold tables included - same bits as one launch per half-sweep"""
+    import torch
+    tuning.setenv("TSU_LATTICE_RESIDENT", "0")
+    n_rep, rows, cols = 21, 70, 1024
+    temps = list(np.linspace(1.5, 3.5, n_rep)) if per_replica_T else 2.269
+    kw = dict(n_replicas=n_rep, temperature=temps, periodic=periodic, seed=31, replica0=5)
+    tuning.setenv("TSU_LATTICE_SPLIT", "1")
+    ref = make_engine(rows, cols, **kw).init_random().sweep(2).sweep(3)
+    for split in (8, 3):
+        tuning.setenv("TSU_LATTICE_SPLIT", str(split))
+        got = make_engine(rows, cols, **kw).init_random().sweep(2).sweep(3)
+        assert torch.equal(got.state, ref.state), split

@@ -769,10 +769,53 @@ int split_ranges(int n_replicas, int rows, int cols) {
   return K;
 }
 
+// Chunks of replicas a batch of lattices is cut into for the same reason (replicas do not depend on each other, so
+// every chunk simply runs its half-sweeps back to back on its own stream).  TSU_LATTICE_SPLIT=1 disables.
+int split_replicas(int n_replicas, int rows, int cols) {
+  if (tuning().split == 1 || n_replicas < 2 * kDefaultSplit) return 1;
+  const double sites = (double)n_replicas * rows * cols;
+  if (tuning().split < 1 && !(sites >= 5e8 && sites <= 6e10)) return 1;
+  return tuning().split > 1 ? (tuning().split < kMaxSplit ? tuning().split : kMaxSplit) : kDefaultSplit;
+}
+
 // the whole-lattice sweeps of tsu_ising2d_sweeps / _sweeps_jit (no halos)
 int launch_sweeps(uint32_t* d_state, int n_replicas, int rows, int cols, int wrap_rows, int wrap_cols, const uint32_t* d_lut,
                   const int32_t* d_lut_index, uint64_t seed, uint32_t sweep0, int n_sweeps, uint32_t replica0,
                   cudaStream_t st, JitKernel jit) {
+  // many replicas: independent chunks of replicas, one stream each, no dependency between them at all
+  const int KR = split_replicas(n_replicas, rows, cols);
+  if (KR > 1 && n_sweeps > 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaEvent_t ev_join;
+    if (cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) return (int)cudaGetLastError();
+    cudaEventRecord(ev_join, st);
+    const size_t rep_words = 2 * (size_t)rows * words_per_row(cols);
+    int rc = TSU_OK;
+    for (int k = 0; k < KR && rc == TSU_OK; ++k) {
+      cudaStream_t sk = k == 0 ? st : slab_stream(dev, k - 1);
+      if (k > 0 && !sk) {  // (the caller's stream may be the default stream: a null handle)
+        rc = (int)cudaErrorUnknown;
+        break;
+      }
+      if (k > 0) cudaStreamWaitEvent(sk, ev_join, 0);
+      const int r0 = (int)((long long)n_replicas * k / KR), r1 = (int)((long long)n_replicas * (k + 1) / KR);
+      for (int t = 0; t < 2 * n_sweeps && rc == TSU_OK; ++t)
+        rc = launch_half_sweep(d_state + (size_t)r0 * rep_words, r1 - r0, rows, cols, wrap_rows, wrap_cols, t & 1, d_lut,
+                               d_lut_index ? d_lut_index + r0 : nullptr, seed, sweep0 + (uint32_t)(t >> 1),
+                               replica0 + (uint32_t)r0, 0, nullptr, nullptr, sk, jit, 0, -1, KR);
+    }
+    for (int k = 1; k < KR; ++k) {  // also after an error: the caller's stream must not run ahead of what was launched
+      cudaStream_t sk = slab_stream(dev, k - 1);
+      if (!sk) break;
+      cudaEventRecord(ev_join, sk);
+      cudaStreamWaitEvent(st, ev_join, 0);
+    }
+    cudaEventDestroy(ev_join);
+    if (rc != TSU_OK) return rc;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? TSU_OK : (int)e;
+  }
   const int K = split_ranges(n_replicas, rows, cols);
   if (K <= 2 || n_sweeps == 0) {
     for (int t = 0; t < 2 * n_sweeps; ++t) {
