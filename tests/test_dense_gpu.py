@@ -331,3 +331,41 @@ def test_tensor_core_multi_panel_multi_sweep_exact(tile_m, monkeypatch):
         want = D.gibbs_sweeps(init[c].astype(int), J, b, T[c], n_sweeps, U)
         bad += int((out[c] != want).any())
     assert bad <= 1, f"{bad} of {C} chains differ (tile height {tile_m})"
+
+
+def test_uniforms_on_the_acceptance_probability_and_clamp_edges():
+    """the float64 kernel decides by logit(u) < h / T and falls back to the reference's u < sigmoid(h / T) when the two
+    sides are close: uniforms placed exactly on p, one ulp below and above it, plus fields on both sides of the +-20
+    clamp (gibbs.py:65-70), must give the reference's bits"""
+    rng = np.random.default_rng(11)
+    N, n_sweeps, T = 24, 6, 0.5
+    # integer couplings, biases in quarters, T = 1/2: every field and h / T is exact in any summation order, so the
+    # kernel's incrementally maintained fields equal the oracle's dot products bit for bit
+    J = rng.integers(-3, 4, size=(N, N)).astype(float)
+    J = np.triu(J, 1)
+    J = J + J.T
+    J[0, 1] = J[1, 0] = 30.0     # fields far beyond the clamp once both are up
+    J[2, 3] = J[3, 2] = -30.0
+    b = rng.integers(-8, 9, size=N) / 4.0
+    b[4] = 20.0 * T              # h / T exactly 20: not clamped (strict >)
+    b[5] = -20.0 * T
+    b[6] = 20.0 * T + 0.25       # just beyond
+    b[7] = -20.0 * T - 0.25
+    for k in (4, 5, 6, 7):
+        J[k, :] = J[:, k] = 0.0
+    s0 = rng.integers(0, 2, N)
+    # walk the oracle and put every uniform on / next to the acceptance probability of its visit
+    state = s0.copy()
+    U = np.zeros((n_sweeps, N))
+    for s in range(n_sweeps):
+        for i in range(N):
+            p = D.sigmoid_ref(float(np.dot(J[i, :], state) + b[i]) / T)
+            choice = (s + i) % 4
+            u = [p, np.nextafter(p, 0.0), np.nextafter(p, 1.0), rng.random()][choice]
+            u = min(max(u, 0.0), np.nextafter(1.0, 0.0))
+            U[s, i] = u
+            state[i] = 1 if u < p else 0
+    want = D.gibbs_sweeps(s0, J, b, T, n_sweeps, U)
+    assert (want == state).all()
+    got = sampler(T, seed=1).gibbs_sweep(s0, J, b, n_sweeps=n_sweeps, _uniforms=U)
+    assert (got == want).all()

@@ -10,11 +10,17 @@
 // run one after the other).
 //
 // The reference recomputes h_i = J[i,:] . s + b_i (O(N)) for every visited site.  Here every chain
-// keeps all N local fields in shared memory; a site visit is O(1) (read h_i, sigmoid, compare) and
-// only an actual flip costs O(N): h_j += J[j,i] * (new - old) for all j, one coalesced row of the
-// transposed coupling matrix read from L2.  The self term J_ii s_i stays part of h_i exactly as in
-// gibbs.py:97.  One __syncthreads per visited site: writes to h_i / s_i of the site just decided
-// are deferred by one step so that slow readers of the same step never race with them.
+// keeps all N local fields in shared memory; a site visit is O(1) (read h_i, compare) and only an
+// actual flip costs O(N): h_j += J[j,i] * (new - old) for all j, one coalesced row of the transposed
+// coupling matrix read from L2 with 2-4 fields per thread, so that a flip costs about one L2 round
+// trip.  With float64 fields the comparison u < sigmoid(h_i / T) is made as logit(u) < h_i / T, the
+// logits of a sweep's uniforms being computed in parallel beforehand; whenever the two sides are
+// within 1e-4 of each other, or near the +-20 clamp, the reference's own expression decides, so the
+// bits are the reference's (tests/test_dense_gpu.py, uniforms placed on and next to p).  The self
+// term J_ii s_i stays part of h_i exactly as in gibbs.py:97.  One __syncthreads per visited site:
+// writes to h_i / s_i of the site just decided are deferred by one step so that slow readers of the
+// same step never race with them.  Per site visit, 296 chains: 0.49 us at N = 512, 0.8 us at 2048,
+// 1.7 us at 4096 (was 2.1 / 2.9 / 5.7 us with 16 fields per thread and the sigmoid in the chain).
 
 #include "common.cuh"
 #include "philox.cuh"
@@ -99,15 +105,21 @@ template <typename JT, typename AT>
 __global__ void dense_gibbs_kernel(DenseParams P) {
   extern __shared__ double smem_d[];
   const int N = P.N;
+  constexpr bool kLogit = sizeof(AT) == sizeof(double);  // float64 fields: decide by logit(u) < h / T where that is safe
   double* u = smem_d;                                   // [N] uniforms of the current sweep (visit order)
-  double* red = u + N;                                  // [32]
+  double* lg = u + N;                                   // [N] logit(u) = log(u) - log(1 - u)   (float64 fields only)
+  double* red = lg + (kLogit ? N : 0);                  // [32]
   AT* h = reinterpret_cast<AT*>(red + 32);              // [N] local fields
-  uint8_t* s = reinterpret_cast<uint8_t*>(h + N);       // [N] bits
+  AT* diag = h + N;                                     // [N] self couplings J_ii
+  uint8_t* s = reinterpret_cast<uint8_t*>(diag + N);    // [N] bits
   const int chain = blockIdx.x;
   const JT* Jt = reinterpret_cast<const JT*>(P.Jt);
   uint8_t* gstate = P.state + (size_t)chain * N;
 
-  for (int j = threadIdx.x; j < N; j += blockDim.x) s[j] = gstate[j] ? 1 : 0;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    s[j] = gstate[j] ? 1 : 0;
+    diag[j] = (AT)Jt[(size_t)j * N + j];
+  }
   __syncthreads();
   compute_fields<JT, AT>(P, s, h);
   __syncthreads();
@@ -140,8 +152,10 @@ __global__ void dense_gibbs_kernel(DenseParams P) {
         const unsigned long long m = (((unsigned long long)o.x << 32) | o.y) >> 11;
         u[idx] = (double)m * (1.0 / 9007199254740992.0);
       }
+      if (kLogit) lg[idx] = log(u[idx]) - log1p(-u[idx]);  // in parallel, off the site-by-site chain (-inf at u = 0)
     }
     __syncthreads();
+    const double invT = 1.0 / Td;
 
     int pend_i = -1;       // site decided in the previous step: its s / self-term writes are deferred
     int pend_bit = 0;
@@ -155,16 +169,36 @@ __global__ void dense_gibbs_kernel(DenseParams P) {
       if (pend_i >= 0) {
         if (threadIdx.x == (pend_i % blockDim.x)) {
           s[pend_i] = (uint8_t)pend_bit;
-          if (pend_delta != (AT)0) h[pend_i] += (AT)Jt[(size_t)pend_i * N + pend_i] * pend_delta;
+          if (pend_delta != (AT)0) h[pend_i] += diag[pend_i] * pend_delta;
         }
       }
-      const AT p = sigmoid_clamped<AT>(hi / T);          // gibbs.py:124-125
-      const int nb = (ui < (double)p) ? 1 : 0;           // gibbs.py:126 (strict <)
+      // gibbs.py:124-126: p = sigmoid(h_i / T) with the +-20 clamp, new bit = u < p (strict).  u < sigmoid(x) <=>
+      // logit(u) < x: the exp and the division leave the sequential chain whenever the two sides are further apart
+      // than anything rounding can do (float64 sigmoid: <= 2e-7 in logit units for |x| < 20; logit(u) and h * (1 / T):
+      // 1e-14); otherwise - and next to the clamps - the reference's expression itself decides.  Same bits.
+      int nb;
+      if (kLogit) {
+        const double xq = (double)hi * invT, t = lg[idx];
+        if (xq > 20.000001)
+          nb = ui < 1.0 ? 1 : 0;                         // x > 20: p = 1.0
+        else if (xq < -20.000001)
+          nb = 0;                                        // x < -20: p = 0.0
+        else if (fabs(xq) < 19.999999 && fabs(xq - t) > 1e-4)
+          nb = t < xq ? 1 : 0;
+        else
+          nb = (ui < (double)sigmoid_clamped<AT>(hi / T)) ? 1 : 0;
+      } else {
+        nb = (ui < (double)sigmoid_clamped<AT>(hi / T)) ? 1 : 0;
+      }
       const AT delta = (AT)(nb - si);
       if (delta != (AT)0) {
         const JT* row = Jt + (size_t)i * N;               // column i of J
-        for (int j = threadIdx.x; j < N; j += blockDim.x)
-          if (j != i) h[j] += (AT)row[j] * delta;
+        // few fields per thread and the loads of one thread batched: a flip costs about one L2 round trip
+#pragma unroll 4
+        for (int j = threadIdx.x; j < N; j += blockDim.x) {
+          const AT v = (AT)__ldg(row + j);
+          if (j != i) h[j] += v * delta;
+        }
       }
       pend_i = i;
       pend_bit = nb;
@@ -173,7 +207,7 @@ __global__ void dense_gibbs_kernel(DenseParams P) {
     }
     if (pend_i >= 0 && threadIdx.x == (pend_i % blockDim.x)) {
       s[pend_i] = (uint8_t)pend_bit;
-      if (pend_delta != (AT)0) h[pend_i] += (AT)Jt[(size_t)pend_i * N + pend_i] * pend_delta;
+      if (pend_delta != (AT)0) h[pend_i] += diag[pend_i] * pend_delta;
     }
     __syncthreads();
 
@@ -277,16 +311,22 @@ __global__ void pt_swap_kernel(const double* __restrict__ energy, const double* 
 }
 
 int pick_threads(int N) {
-  int t = (N + 15) / 16;        // about 16 fields per thread
+  // fields per thread: a flip adds one row of Jt to the fields and costs about one L2 round trip when every thread has
+  // its few loads in flight at once (measured per site visit, 296 chains: N = 512: 2 per thread 490 ns, 4: 615, 16: 1655;
+  // N = 2048: 2: 1273, 4: 722, 16: 1640; N = 4096: 4: 1699, 8: 2169, 16: 3360).  TSU_DENSE_FPT overrides.
+  static const int forced = getenv("TSU_DENSE_FPT") ? atoi(getenv("TSU_DENSE_FPT")) : 0;
+  const int per_thread = forced > 0 ? forced : (N <= 512 ? 2 : 4);
+  int t = (N + per_thread - 1) / per_thread;
   t = (t + 31) / 32 * 32;
   if (t < 32) t = 32;
-  if (t > 512) t = 512;
+  if (t > 1024) t = 1024;
   return t;
 }
 
 template <typename JT, typename AT>
 int launch_dense(const DenseParams& P, cudaStream_t st) {
-  const size_t smem = sizeof(double) * ((size_t)P.N + 32) + sizeof(AT) * (size_t)P.N + (size_t)P.N + 16;
+  const size_t smem = sizeof(double) * ((size_t)P.N * (sizeof(AT) == sizeof(double) ? 2 : 1) + 32) +
+                      2 * sizeof(AT) * (size_t)P.N + (size_t)P.N + 16;
   if (smem > 227 * 1024) return TSU_ERR_UNSUPPORTED;
   if (smem > 48 * 1024) {
     cudaError_t e =
