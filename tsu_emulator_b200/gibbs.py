@@ -93,9 +93,14 @@ class _TcProblem:
         if update_order != "sequential":
             raise ValueError("precision='bf16' (tensor-core path) implements the sequential update order only")
         self.device = device
-        Jp = np.zeros((self.Np, self.Np), dtype=np.float32)
-        Jp[:self.N, :self.N] = J
-        self.J = torch.from_numpy(Jp).to(device=device, dtype=torch.bfloat16).contiguous()
+        # upload as given and round on the device (float64 -> float32 -> bf16, the rounding the oracle applies): the
+        # host-side conversion of a 4096 x 4096 matrix used to cost several times the 10 sweeps it was uploaded for
+        Jd = torch.from_numpy(np.ascontiguousarray(J)).to(device).to(torch.float32).to(torch.bfloat16)
+        if self.Np != self.N:
+            Jp = torch.zeros((self.Np, self.Np), dtype=torch.bfloat16, device=device)
+            Jp[:self.N, :self.N] = Jd
+            Jd = Jp
+        self.J = Jd.contiguous()
         self.bias = None
         if bias is not None:
             b = np.asarray(bias, dtype=np.float64)
