@@ -41,6 +41,11 @@ class GibbsConfig:
             raise ValueError("Update order must be 'sequential' or 'random'")
 
 
+def _host_int64(t) -> np.ndarray:
+    """device bits -> the reference's int arrays (gibbs.py:207 `np.zeros(..., dtype=int)`)"""
+    return t.cpu().numpy().astype(np.int64)
+
+
 def _as_square(coupling) -> np.ndarray:
     J = np.asarray(coupling, dtype=np.float64)
     n_bits = J.shape[0]
@@ -308,7 +313,7 @@ class GibbsSampler:
             self.sample_count += int(n_samples)
             if as_tensor:
                 return samples if n_chains > 1 else samples[:, 0]
-            out = samples.cpu().numpy().astype(int)
+            out = _host_int64(samples)
             return out[:, 0, :] if n_chains == 1 else np.ascontiguousarray(out.transpose(1, 0, 2))
         if self.precision == "bf16":
             if _uniforms is not None or _orders is not None:
@@ -324,7 +329,7 @@ class GibbsSampler:
         self.sample_count += int(n_samples)
         if as_tensor:
             return samples if n_chains > 1 else samples[:, 0]
-        out = samples.cpu().numpy().astype(int)  # (n_samples, n_chains, N)
+        out = _host_int64(samples)  # (n_samples, n_chains, N)
         if n_chains == 1:
             return out[:, 0, :]
         return np.ascontiguousarray(out.transpose(1, 0, 2))
@@ -360,7 +365,7 @@ class GibbsSampler:
         self.sample_count += n_samples
         if as_tensor:
             return samples if n_chains > 1 else samples[:, 0]
-        out = samples.cpu().numpy().astype(int)
+        out = _host_int64(samples)
         if n_chains == 1:
             return out[:, 0, :]
         return np.ascontiguousarray(out.transpose(1, 0, 2))
@@ -384,7 +389,7 @@ class GibbsSampler:
             if prob.bias is not None:
                 energy = energy - sf @ prob.bias.to(torch.float64)
         st = st[:, :N]
-        out = st if as_tensor else st.cpu().numpy().astype(int)
+        out = st if as_tensor else _host_int64(st)
         if return_energy:
             return out, (energy if as_tensor else energy.cpu().numpy())
         return out
@@ -404,7 +409,7 @@ class GibbsSampler:
         _, energy, _, _ = self._run(prob, st, n_burnin=n_sweeps, n_samples=0, sweeps_per_sample=0,
                                     want_energy=return_energy)
         self._chain_counter += int(n_chains)
-        out = st if as_tensor else st.cpu().numpy().astype(int)
+        out = st if as_tensor else _host_int64(st)
         if return_energy:
             return out, (energy if as_tensor else energy.cpu().numpy())
         return out
@@ -463,7 +468,7 @@ class GibbsSampler:
         self._chain_counter += R
         st = stats.cpu().numpy()
         sr = slot_replica.cpu().numpy()
-        states_np = states.cpu().numpy().astype(int)
+        states_np = _host_int64(states)
         en = energies.cpu().numpy()
         info = {
             "swap_acceptance_rate": (st[1] / st[0]) if st[0] > 0 else 0,
@@ -472,7 +477,7 @@ class GibbsSampler:
             "energies": [list(en[:, i]) for i in range(R)],
             "final_states": [states_np[sr[i]] for i in range(R)],
         }
-        return samples.cpu().numpy().astype(int), info
+        return _host_int64(samples), info
 
     def simulated_annealing(self, coupling: np.ndarray, bias: Optional[np.ndarray] = None, T_initial: float = 10.0,
                             T_final: float = 0.1, n_steps: int = 1000, cooling_schedule: str = "exponential", *,
@@ -505,9 +510,9 @@ class GibbsSampler:
                                                           uniforms=u)
             be = best_energy.cpu().numpy()
             k = int(np.argmin(be))
-            state = best_state[k].cpu().numpy().astype(int)
+            state = _host_int64(best_state[k])
         else:
-            state = st[0].cpu().numpy().astype(int)
+            state = _host_int64(st[0])
         self._chain_counter += int(n_chains)
         if chromatic:
             from .sparse import to_csr
