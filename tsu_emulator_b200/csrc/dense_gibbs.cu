@@ -236,6 +236,121 @@ __global__ void dense_gibbs_kernel(DenseParams P) {
   if (P.track_best && threadIdx.x == 0) P.best_energy[chain] = best_e;
 }
 
+// ---- models of at most 32 bits: one WARP per chain ---------------------------------------------------------
+// The reference's published benchmarks (tsu/benchmarks/sampling.py, optimization.py: 1-20 bits, one chain, up to 10^5
+// sweeps per call) are pure latency: a visit of the kernel above is a block barrier and shared-memory round trips
+// (~340 ns).  Here lane j keeps field h_j in a register, the bits are a warp-uniform mask, the couplings sit in shared
+// memory and a visit is one shuffle, one compare and one FMA.  Same arithmetic in the same order as the kernel above
+// (initial fields summed over ascending k, one J * delta added per flip, the energy reduced by the same xor shuffles),
+// so the bits, energies and best states are identical (goldens dense_*_n8 ... n14, tempering_n10).
+constexpr int kWarpChainMaxN = 32;
+constexpr int kWarpChainsPerCta = 4;
+
+template <typename JT>
+__global__ void __launch_bounds__(32 * kWarpChainsPerCta) dense_gibbs_warp_kernel(DenseParams P) {
+  extern __shared__ double smem_d[];
+  const int N = P.N;
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  double* Jsm = smem_d;                                  // [N][N] Jt as double: Jsm[i * N + j] = J[j][i]
+  double* lg = Jsm + N * N + wic * 64;                   // [32] logit(u) of this warp's current sweep (visit order)
+  double* u = lg + 32;                                   // [32] the uniforms themselves (exact fallback)
+  const JT* Jt = reinterpret_cast<const JT*>(P.Jt);
+  const JT* b = reinterpret_cast<const JT*>(P.bias);
+  for (int k = threadIdx.x; k < N * N; k += blockDim.x) Jsm[k] = (double)Jt[k];
+  __syncthreads();
+  const int chain = blockIdx.x * kWarpChainsPerCta + wic;
+  if (chain >= P.n_chains) return;
+  const bool mine = lane < N;
+  uint8_t* gstate = P.state + (size_t)chain * N;
+  const uint32_t my_bit = mine && gstate[lane] ? 1u : 0u;
+  uint32_t mask = __ballot_sync(0xffffffffu, my_bit != 0u);   // bit j = s_j, the same in every lane
+  const double bj = (mine && b) ? (double)b[lane] : 0.0;
+  double h = 0.0;
+  if (mine) {
+    for (int k = 0; k < N; ++k)
+      if ((mask >> k) & 1u) h += Jsm[k * N + lane];      // h_j = sum_k J[j][k] s_k (ascending k)
+    if (b) h += bj;
+  }
+  auto energy_now = [&]() {                               // -1/2 sum_j s_j h_j - 1/2 sum_j b_j s_j, as chain_energy()
+    double acc = 0.0;
+    if (mine && ((mask >> lane) & 1u)) acc += -0.5 * h - (b ? 0.5 * bj : 0.0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return 0.0 + acc;
+  };
+  double best_e = 0.0;
+  if (P.track_best) {
+    best_e = energy_now();
+    if (mine) P.best_state[(size_t)chain * N + lane] = (uint8_t)((mask >> lane) & 1u);
+  }
+  const int total = P.n_burnin + P.n_samples * P.sweeps_per_sample;
+  int next_sample_at = P.n_burnin + P.sweeps_per_sample;
+  int sample_idx = 0;
+  const int NV = P.n_visit;
+  for (int sw = 0; sw < total; ++sw) {
+    const double T = P.T_chain ? P.T_chain[chain] : (P.T_sweep ? P.T_sweep[sw] : P.T);
+    const double invT = 1.0 / T;
+    // this sweep's visiting order (lane idx holds the site of visit idx) and uniforms
+    int site_l = lane;
+    if (lane < NV) {
+      if (P.order) site_l = P.order[(size_t)sw * NV + lane];
+      double ui;
+      if (P.uniforms) {
+        ui = P.uniforms[((size_t)sw * P.n_chains + chain) * NV + lane];
+      } else {
+        tsu_u32x4 o = tsu_philox4x32_10((uint32_t)site_l, P.chain0 + (uint32_t)chain, P.sweep0 + (uint32_t)sw,
+                                        TSU_STREAM_DENSE, P.k0, P.k1);
+        const unsigned long long m = (((unsigned long long)o.x << 32) | o.y) >> 11;
+        ui = (double)m * (1.0 / 9007199254740992.0);
+      }
+      u[lane] = ui;
+      lg[lane] = log(ui) - log1p(-ui);
+    }
+    __syncwarp();
+    for (int idx = 0; idx < NV; ++idx) {
+      const int i = __shfl_sync(0xffffffffu, site_l, idx);
+      const double hi = __shfl_sync(0xffffffffu, h, i);
+      const int si = (int)((mask >> i) & 1u);
+      const double ui = u[idx], t = lg[idx];
+      const double xq = hi * invT;                       // decision exactly as in dense_gibbs_kernel (float64 fields)
+      int nb;
+      if (xq > 20.000001)
+        nb = ui < 1.0 ? 1 : 0;
+      else if (xq < -20.000001)
+        nb = 0;
+      else if (fabs(xq) < 19.999999 && fabs(xq - t) > 1e-4)
+        nb = t < xq ? 1 : 0;
+      else
+        nb = (ui < sigmoid_clamped<double>(hi / T)) ? 1 : 0;
+      const double delta = (double)(nb - si);
+      if (delta != 0.0) {
+        if (mine) h += Jsm[i * N + lane] * delta;        // every field incl. the self term J_ii (gibbs.py:97)
+        mask ^= 1u << i;
+      }
+    }
+    __syncwarp();                                        // u / lg are rewritten by the next sweep
+    if (P.track_best) {                                  // gibbs.py:387-391
+      const double e = energy_now();
+      if (e < best_e) {
+        best_e = e;
+        if (mine) P.best_state[(size_t)chain * N + lane] = (uint8_t)((mask >> lane) & 1u);
+      }
+    }
+    if (sw + 1 == next_sample_at) {
+      if (P.samples && sample_idx < P.n_samples && mine)
+        P.samples[((size_t)sample_idx * P.n_chains + chain) * N + lane] = (uint8_t)((mask >> lane) & 1u);
+      ++sample_idx;
+      next_sample_at += P.sweeps_per_sample;
+    }
+  }
+  if (mine) gstate[lane] = (uint8_t)((mask >> lane) & 1u);
+  if (P.energy) {
+    const double e = energy_now();
+    if (lane == 0) P.energy[chain] = e;
+  }
+  if (P.track_best && lane == 0) P.best_energy[chain] = best_e;
+}
+
 // E = -1/2 s^T J s - b^T s from scratch, float64 accumulation (tsu/gibbs.py:215-236)
 template <typename JT>
 __global__ void dense_energy_kernel(const JT* __restrict__ Jt, const JT* __restrict__ bias,
@@ -325,6 +440,14 @@ int pick_threads(int N) {
 
 template <typename JT, typename AT>
 int launch_dense(const DenseParams& P, cudaStream_t st) {
+  static const bool no_warp_kernel = getenv("TSU_DENSE_NO_WARP") != nullptr;  // launch shape only: same bits
+  if (sizeof(AT) == sizeof(double) && P.N <= kWarpChainMaxN && !no_warp_kernel) {
+    const size_t smem = sizeof(double) * ((size_t)P.N * P.N + 64 * kWarpChainsPerCta);
+    dense_gibbs_warp_kernel<JT><<<(P.n_chains + kWarpChainsPerCta - 1) / kWarpChainsPerCta, 32 * kWarpChainsPerCta, smem,
+                                  st>>>(P);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? TSU_OK : (int)e;
+  }
   const size_t smem = sizeof(double) * ((size_t)P.N * (sizeof(AT) == sizeof(double) ? 2 : 1) + 32) +
                       2 * sizeof(AT) * (size_t)P.N + (size_t)P.N + 16;
   if (smem > 227 * 1024) return TSU_ERR_UNSUPPORTED;
