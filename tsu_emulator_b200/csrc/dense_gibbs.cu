@@ -287,31 +287,39 @@ __global__ void __launch_bounds__(32 * kWarpChainsPerCta) dense_gibbs_warp_kerne
   int next_sample_at = P.n_burnin + P.sweeps_per_sample;
   int sample_idx = 0;
   const int NV = P.n_visit;
+  // visiting order and uniforms (with their logits: two float64 logarithms, most of a short sweep's time) are produced
+  // for as many sweeps at once as fit the 32 lanes: lane l serves visit l % NV of sweep sw + l / NV
+  const int batch = 32 / NV > 0 ? 32 / NV : 1;
+  const int l_sweep = lane / NV, l_visit = lane - l_sweep * NV;
+  int site_l = lane;
   for (int sw = 0; sw < total; ++sw) {
     const double T = P.T_chain ? P.T_chain[chain] : (P.T_sweep ? P.T_sweep[sw] : P.T);
     const double invT = 1.0 / T;
-    // this sweep's visiting order (lane idx holds the site of visit idx) and uniforms
-    int site_l = lane;
-    if (lane < NV) {
-      if (P.order) site_l = P.order[(size_t)sw * NV + lane];
-      double ui;
-      if (P.uniforms) {
-        ui = P.uniforms[((size_t)sw * P.n_chains + chain) * NV + lane];
-      } else {
-        tsu_u32x4 o = tsu_philox4x32_10((uint32_t)site_l, P.chain0 + (uint32_t)chain, P.sweep0 + (uint32_t)sw,
-                                        TSU_STREAM_DENSE, P.k0, P.k1);
-        const unsigned long long m = (((unsigned long long)o.x << 32) | o.y) >> 11;
-        ui = (double)m * (1.0 / 9007199254740992.0);
+    const int in_batch = sw % batch;
+    if (in_batch == 0) {
+      const int my_sw = sw + l_sweep;
+      if (l_sweep < batch && my_sw < total) {
+        site_l = P.order ? P.order[(size_t)my_sw * NV + l_visit] : l_visit;
+        double ui;
+        if (P.uniforms) {
+          ui = P.uniforms[((size_t)my_sw * P.n_chains + chain) * NV + l_visit];
+        } else {
+          tsu_u32x4 o = tsu_philox4x32_10((uint32_t)site_l, P.chain0 + (uint32_t)chain, P.sweep0 + (uint32_t)my_sw,
+                                          TSU_STREAM_DENSE, P.k0, P.k1);
+          const unsigned long long m = (((unsigned long long)o.x << 32) | o.y) >> 11;
+          ui = (double)m * (1.0 / 9007199254740992.0);
+        }
+        u[lane] = ui;
+        lg[lane] = log(ui) - log1p(-ui);
       }
-      u[lane] = ui;
-      lg[lane] = log(ui) - log1p(-ui);
+      __syncwarp();
     }
-    __syncwarp();
+    const int l0 = in_batch * NV;                        // first lane of this sweep's visits
     for (int idx = 0; idx < NV; ++idx) {
-      const int i = __shfl_sync(0xffffffffu, site_l, idx);
+      const int i = __shfl_sync(0xffffffffu, site_l, l0 + idx);
       const double hi = __shfl_sync(0xffffffffu, h, i);
       const int si = (int)((mask >> i) & 1u);
-      const double ui = u[idx], t = lg[idx];
+      const double ui = u[l0 + idx], t = lg[l0 + idx];
       const double xq = hi * invT;                       // decision exactly as in dense_gibbs_kernel (float64 fields)
       int nb;
       if (xq > 20.000001)
