@@ -416,15 +416,19 @@ def run_secondary(torch, dist, world, rank, local_rank, peaks):
             J = (J + J.T) / np.sqrt(2)
             np.fill_diagonal(J, 0)
             smp = GibbsSampler(GibbsConfig(temperature=1.0, n_sweeps=SW), seed=seed, precision="bf16")
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            st = smp.sample_chains(J, None, n_chains=2048, n_sweeps=SW, as_tensor=True)
-            torch.cuda.synchronize()
-            api_ms = (time.perf_counter() - t0) * 1e3
+            api = []
+            for _ in range(2):  # the first call also pays lazy kernel loading, allocator growth, the tensor map
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                st = smp.sample_chains(J, None, n_chains=2048, n_sweeps=SW, as_tensor=True)
+                torch.cuda.synchronize()
+                api.append((time.perf_counter() - t0) * 1e3)
+            api_ms = api[1]
             Jd = torch.from_numpy(J).cuda().to(torch.bfloat16).contiguous()
             n_sm = torch.cuda.get_device_properties(0).multi_processor_count
             res = {"workload": f"GibbsSampler(precision='bf16') dense SK couplings (bf16) N={N}, sequential sweeps, tcgen05 + TMEM",
-                   "api_ms_2048_chains_10_sweeps_incl_J_upload": api_ms, "mean_bit": float(st.float().mean())}
+                   "api_ms_2048_chains_10_sweeps_incl_J_upload": api_ms, "api_ms_first_call": api[0],
+                   "mean_bit": float(st.float().mean())}
             for C, tag in ((2048, "2048_chains"), (128 * n_sm, "full_wave_%d_chains" % (128 * n_sm))):
                 s_ = (torch.rand(C, N, device="cuda") < 0.5).to(torch.uint8)
                 _lib.call("tsu_dense_gibbs_tc_run", _lib.ptr(Jd), None, _lib.ptr(s_), C, N, 1.0, None, 1, seed, 0, 0, None,
