@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(32 * kWarpChainsPerCta) dense_gibbs_warp_kerne
       const double hi = __shfl_sync(0xffffffffu, h, i);
       const int si = (int)((mask >> i) & 1u);
       const double ui = u[l0 + idx], t = lg[l0 + idx];
+      const double jv = mine ? Jsm[i * N + lane] : 0.0;  // J[lane][i], fetched before the decision is known
       const double xq = hi * invT;                       // decision exactly as in dense_gibbs_kernel (float64 fields)
       int nb;
       if (xq > 20.000001)
@@ -330,9 +331,8 @@ __global__ void __launch_bounds__(32 * kWarpChainsPerCta) dense_gibbs_warp_kerne
         nb = t < xq ? 1 : 0;
       else
         nb = (ui < sigmoid_clamped<double>(hi / T)) ? 1 : 0;
-      const double delta = (double)(nb - si);
-      if (delta != 0.0) {
-        if (mine) h += Jsm[i * N + lane] * delta;        // every field incl. the self term J_ii (gibbs.py:97)
+      if (nb != si) {                                    // h_j += J[j][i] * (new - old): +-J exactly, every field
+        h += nb ? jv : -jv;                              // incl. the self term J_ii (gibbs.py:97)
         mask ^= 1u << i;
       }
     }
