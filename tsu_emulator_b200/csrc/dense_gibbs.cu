@@ -102,7 +102,7 @@ __device__ double chain_energy(const DenseParams& P, const uint8_t* s, const AT*
 }
 
 template <typename JT, typename AT>
-__global__ void dense_gibbs_kernel(DenseParams P) {
+__global__ void __launch_bounds__(1024) dense_gibbs_kernel(DenseParams P) {  // pick_threads() goes up to 1024
   extern __shared__ double smem_d[];
   const int N = P.N;
   constexpr bool kLogit = sizeof(AT) == sizeof(double);  // float64 fields: decide by logit(u) < h / T where that is safe
